@@ -1,0 +1,322 @@
+"""B200 backend with the names and positional signatures of the reference's flat kernels.
+
+This module is what plugs into the reference's backend seam (src/CSparse3/csc.py:33-41):
+
+    if __config__.NATIVE: from CSparse3.csc_native import *   ->   from csparse3_b200.csc_b200 import *
+    import scipy.sparse.sparsetools as sptools                ->   from csparse3_b200.csc_b200 import sptools
+
+Every numeric function forwards to libcsparse3_b200.so (CUDA, sm_100a) through ctypes with HOST numpy
+buffers, exactly like the numba kernels take them; device-resident batched work goes through
+csparse3_b200.lu / csparse3_b200.spmv instead.  dtype strictness follows the reference's eager numba
+signatures (i8 scalars, i4[:] indices, f8[:] values).
+
+The last block of helpers (dense conversion, diagonals, stacking, sub-matrices, islands) is host-side
+assembly glue that the reference also runs outside the numeric loop; it is plain numpy and never used by
+the refactor / solve / multiply path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import as_f64, as_i32, check, ptr
+
+__all__ = [
+    "csc_mat_vec_ff", "csc_multiply_ff", "csc_transpose", "csc_to_csr", "csc_cumsum_i", "sptools",
+    "csc_amd", "csc_etree", "csc_post", "csc_lu", "csc_lu_refactor", "csc_lu_solve", "csc_lusol",
+    "csc_to_dense", "csc_diagonal", "csc_diagonal_from_array", "csc_stack_4_by_4_ff", "csc_sub_matrix",
+    "csc_sub_matrix_cols", "csc_sub_matrix_rows", "csc_norm", "find_islands", "coo_to_csc",
+]
+
+
+# ---- numeric hot path (CUDA) -----------------------------------------------------------------------------
+
+def csc_mat_vec_ff(m, n, Ap, Ai, Ax, x):
+    """y = A * x.  Reference: csc_numba.py:309-328 (same signature, returns a fresh y)."""
+    Ap, Ai, Ax, x = as_i32(Ap, "Ap"), as_i32(Ai, "Ai"), as_f64(Ax, "Ax"), as_f64(x, "x")
+    assert n == x.shape[0]
+    y = np.empty(m, dtype=np.float64)
+    check(_lib.lib().csp3_csc_mat_vec_ff_host(m, n, ptr(Ap), ptr(Ai), ptr(Ax), ptr(x), ptr(y)), "csc_mat_vec_ff")
+    return y
+
+
+def csc_multiply_ff(Am, An, Ap, Ai, Ax, Bm, Bn, Bp, Bi, Bx):
+    """C = A * B -> (Cm, Cn, Cp, Ci, Cx, nnz).  Reference: csc_numba.py:222-306.
+    Cp and nnz are identical to the reference (explicit zeros kept); row indices inside each column come
+    out SORTED (the reference's order is first-touch)."""
+    assert An == Bm
+    Ap, Ai, Ax = as_i32(Ap, "Ap"), as_i32(Ai, "Ai"), as_f64(Ax, "Ax")
+    Bp, Bi, Bx = as_i32(Bp, "Bp"), as_i32(Bi, "Bi"), as_f64(Bx, "Bx")
+    L = _lib.lib()
+    Cp = np.empty(Bn + 1, dtype=np.int32)
+    nnz = C.c_int64(0)
+    check(L.csp3_spgemm_symbolic_host(Am, An, ptr(Ap), ptr(Ai), Bm, Bn, ptr(Bp), ptr(Bi), ptr(Cp), C.byref(nnz)),
+          "csc_multiply_ff (symbolic)")
+    Ci = np.empty(nnz.value, dtype=np.int32)
+    Cx = np.empty(nnz.value, dtype=np.float64)
+    check(L.csp3_spgemm_numeric_host(Am, An, ptr(Ap), ptr(Ai), ptr(Ax), Bm, Bn, ptr(Bp), ptr(Bi), ptr(Bx),
+                                     ptr(Cp), ptr(Ci), ptr(Cx)), "csc_multiply_ff (numeric)")
+    return Am, Bn, Cp, Ci, Cx, int(nnz.value)
+
+
+def csc_transpose(m, n, Ap, Ai, Ax):
+    """C = A' -> (Cm, Cn, Cp, Ci, Cx).  Reference: csc_numba.py:400-436."""
+    Ap, Ai, Ax = as_i32(Ap, "Ap"), as_i32(Ai, "Ai"), as_f64(Ax, "Ax")
+    nnz = int(Ap[n])
+    Cp = np.empty(m + 1, dtype=np.int32)
+    Ci = np.empty(nnz, dtype=np.int32)
+    Cx = np.empty(nnz, dtype=np.float64)
+    check(_lib.lib().csp3_csc_transpose_host(m, n, ptr(Ap), ptr(Ai), ptr(Ax[:max(nnz, 0)]) if nnz else None,
+                                             ptr(Cp), ptr(Ci), ptr(Cx)), "csc_transpose")
+    return n, m, Cp, Ci, Cx
+
+
+def csc_to_csr(m, n, Ap, Ai, Ax, Bp, Bi, Bx):
+    """Fill caller-allocated CSR arrays.  Reference: csc_numba.py:360-397 (void, outputs preallocated)."""
+    Ap, Ai, Ax = as_i32(Ap, "Ap"), as_i32(Ai, "Ai"), as_f64(Ax, "Ax")
+    for a, dt in ((Bp, np.int32), (Bi, np.int32), (Bx, np.float64)):
+        if a.dtype != dt or not a.flags.c_contiguous:
+            raise TypeError("csc_to_csr outputs must be contiguous int32/int32/float64 arrays")
+    check(_lib.lib().csp3_csc_to_csr_host(m, n, ptr(Ap), ptr(Ai), ptr(Ax), ptr(Bp), ptr(Bi), ptr(Bx)), "csc_to_csr")
+
+
+def csc_cumsum_i(p, c, n):
+    """p[0..n] = cumsum(c), c <- p[0..n-1]; returns sum(c).  Reference: csc_numba.py:75-94 (host helper)."""
+    np.cumsum(c[:n], out=p[1:n + 1])
+    p[0] = 0
+    c[:n] = p[:n]
+    return int(p[n])
+
+
+class _SpTools:
+    """Stand-in for the `sptools` module the reference imports at csc.py:33 (scipy.sparse.sparsetools):
+    same names, argument order and in-place output convention (src/sparsetools/csc.h)."""
+
+    @staticmethod
+    def csc_matvec(n_row, n_col, Ap, Ai, Ax, Xx, Yx):
+        """Yx += A * Xx.  csc.h:27-45, call site csc.py:374-379."""
+        Ap, Ai, Ax, Xx = as_i32(Ap, "Ap"), as_i32(Ai, "Ai"), as_f64(Ax, "Ax"), as_f64(Xx, "Xx")
+        if Yx.dtype != np.float64 or not Yx.flags.c_contiguous:
+            raise ValueError("Yx must be a contiguous float64 array")
+        check(_lib.lib().csp3_csc_matvec_host(n_row, n_col, ptr(Ap), ptr(Ai), ptr(Ax), ptr(Xx), ptr(Yx)), "csc_matvec")
+
+    @staticmethod
+    def csc_matvecs(n_row, n_col, n_vecs, Ap, Ai, Ax, Xx, Yx):
+        """Yx[n_row,n_vecs] += A * Xx[n_col,n_vecs].  csc.h:68-84, call site csc.py:409-415."""
+        Ap, Ai, Ax, Xx = as_i32(Ap, "Ap"), as_i32(Ai, "Ai"), as_f64(Ax, "Ax"), as_f64(Xx, "Xx")
+        if Yx.dtype != np.float64 or not Yx.flags.c_contiguous:
+            raise ValueError("Yx must be a contiguous float64 array")
+        check(_lib.lib().csp3_csc_matvecs_host(n_row, n_col, n_vecs, ptr(Ap), ptr(Ai), ptr(Ax), ptr(Xx), ptr(Yx)),
+              "csc_matvecs")
+
+    @staticmethod
+    def csc_matmat_pass1(n_row, n_col, Ap, Ai, Bp, Bi, Cp):
+        """Column pointer of C = A*B.  csc.h:115-123; n_row = rows of A, n_col = columns of B.
+        (Structural count, like pass 1 of SMMP: cancellations are not anticipated.)"""
+        Ap, Ai, Bp, Bi = as_i32(Ap, "Ap"), as_i32(Ai, "Ai"), as_i32(Bp, "Bp"), as_i32(Bi, "Bi")
+        An = len(Ap) - 1
+        nnz = C.c_int64(0)
+        rc = _lib.lib().csp3_spgemm_symbolic_host(n_row, An, ptr(Ap), ptr(Ai), An, n_col, ptr(Bp), ptr(Bi), ptr(Cp),
+                                                  C.byref(nnz))
+        if rc == -4:
+            raise RuntimeError("nnz of the result is too large")       # std::overflow_error -> RuntimeError
+        check(rc, "csc_matmat_pass1")
+
+    @staticmethod
+    def csc_matmat_pass2(n_row, n_col, Ap, Ai, Ax, Bp, Bi, Bx, Cp, Ci, Cx):
+        """Entries of C = A*B given pass 1's Cp.  csc.h:125-137 -> csr.h:608-670: exact zeros are dropped and
+        Cp is rewritten accordingly (row indices come out sorted; scipy emits reverse first-touch order)."""
+        Ap, Ai, Ax = as_i32(Ap, "Ap"), as_i32(Ai, "Ai"), as_f64(Ax, "Ax")
+        Bp, Bi, Bx = as_i32(Bp, "Bp"), as_i32(Bi, "Bi"), as_f64(Bx, "Bx")
+        An = len(Ap) - 1
+        check(_lib.lib().csp3_spgemm_numeric_host(n_row, An, ptr(Ap), ptr(Ai), ptr(Ax), An, n_col, ptr(Bp), ptr(Bi),
+                                                  ptr(Bx), ptr(Cp), ptr(Ci), ptr(Cx)), "csc_matmat_pass2")
+        nnz = int(Cp[n_col])
+        keep = Cx[:nnz] != 0
+        if not keep.all():                                               # output-format step only (csr.h:655)
+            col = np.repeat(np.arange(n_col), np.diff(Cp[:n_col + 1]))[keep]
+            k = int(keep.sum())
+            Ci[:k] = Ci[:nnz][keep]
+            Cx[:k] = Cx[:nnz][keep]
+            Cp[:] = np.concatenate([[0], np.cumsum(np.bincount(col, minlength=n_col))]).astype(np.int32)
+
+
+sptools = _SpTools()
+
+
+# ---- LU / solve (no reference counterpart; CSparse semantics) -----------------------------
+
+def csc_amd(order, m, n, Ap, Ai):
+    """q = amd(order, A) -> int32[n] (CSparse cs_amd; host symbolic phase)."""
+    Ap, Ai = as_i32(Ap, "Ap"), as_i32(Ai, "Ai")
+    q = np.empty(max(n, 1), dtype=np.int32)
+    check(_lib.lib().csp3_csc_amd(order, m, n, ptr(Ap), ptr(Ai), ptr(q)), "csc_amd")
+    return q[:n]
+
+
+def csc_etree(m, n, Ap, Ai, ata=False):
+    """parent = etree(A) or etree(A'A) -> int32[n] (CSparse cs_etree)."""
+    Ap, Ai = as_i32(Ap, "Ap"), as_i32(Ai, "Ai")
+    parent = np.empty(max(n, 1), dtype=np.int32)
+    check(_lib.lib().csp3_csc_etree(m, n, ptr(Ap), ptr(Ai), int(bool(ata)), ptr(parent)), "csc_etree")
+    return parent[:n]
+
+
+def csc_post(n, parent):
+    """post = postorder(parent) -> int32[n] (CSparse cs_post)."""
+    parent = as_i32(parent, "parent")
+    post = np.empty(max(n, 1), dtype=np.int32)
+    check(_lib.lib().csp3_csc_post(n, ptr(parent), ptr(post)), "csc_post")
+    return post[:n]
+
+
+def csc_lu(n, Ap, Ai, Ax, q, tol):
+    """First factorisation -> (Lp, Li, Lx, Up, Ui, Ux, pinv) in the CSparse cs_lu layout.  The pivot
+    sequence and patterns come from the host symbolic phase; the returned VALUES are recomputed by the
+    CUDA refactor kernel."""
+    from .lu import LuSymbolic
+    sym = LuSymbolic(n, Ap, Ai, Ax, q=q, tol=tol)
+    Lx, Ux, status = sym.refactor_host(np.asarray(Ax, dtype=np.float64)[None, :])
+    if status[0]:
+        raise ArithmeticError("zero or non-finite pivot in column %d" % (status[0] - 1))
+    return sym.Lp, sym.Li, Lx[0], sym.Up, sym.Ui, Ux[0], sym.pinv
+
+
+def csc_lu_refactor(n, Ap, Ai, Ax, q, pinv, Lp, Li, Up, Ui):
+    """Refactor with frozen pattern and pivots -> (Lx, Ux)."""
+    from .lu import LuSymbolic
+    sym = LuSymbolic.from_pattern(n, Ap, Ai, q, pinv, Lp, Li, Up, Ui)
+    Lx, Ux, status = sym.refactor_host(np.asarray(Ax, dtype=np.float64)[None, :])
+    if status[0]:
+        raise ArithmeticError("zero or non-finite pivot in column %d" % (status[0] - 1))
+    return Lx[0], Ux[0]
+
+
+def csc_lu_solve(n, Ap, Ai, q, pinv, Lp, Li, Lx, Up, Ui, Ux, b):
+    """x = Q (U \\ (L \\ (P b))) with existing factors (tail of CSparse cs_lusol)."""
+    from .lu import LuSymbolic
+    sym = LuSymbolic.from_pattern(n, Ap, Ai, q, pinv, Lp, Li, Up, Ui)
+    return sym.solve_host(as_f64(Lx)[None, :], as_f64(Ux)[None, :], as_f64(b)[None, :])[0]
+
+
+def csc_lusol(order, n, Ap, Ai, Ax, b, tol):
+    """x = A \\ b (CSparse cs_lusol): analyse on the host, refactor + solve on the GPU."""
+    Ap, Ai, Ax = as_i32(Ap, "Ap"), as_i32(Ai, "Ai"), as_f64(Ax, "Ax")
+    x = as_f64(b, "b").copy()
+    check(_lib.lib().csp3_csc_lusol_host(order, n, ptr(Ap), ptr(Ai), ptr(Ax), ptr(x), float(tol)), "csc_lusol")
+    return x
+
+
+# ---- host-side assembly glue (numpy; outside the numeric loop, reference marks these OUT of the hot path) ----
+
+def csc_to_dense(m, n, indptr, indices, data):
+    """csc_numba.py:581-597 (last duplicate wins, like the reference's assignment loop)."""
+    val = np.zeros((m, n), dtype=np.float64)
+    cols = np.repeat(np.arange(n), np.diff(np.asarray(indptr)[:n + 1]))
+    nnz = int(indptr[n])
+    val[np.asarray(indices)[:nnz], cols] = np.asarray(data)[:nnz]
+    return val
+
+
+def csc_diagonal(m, value=1.0):
+    """csc_numba.py:600-617 -> (indices, indptr, data)"""
+    return np.arange(m, dtype=np.int32), np.arange(m + 1, dtype=np.int32), np.full(m, value, dtype=np.float64)
+
+
+def csc_diagonal_from_array(m, array):
+    """csc_numba.py:620-637 -> (indices, indptr, data)"""
+    return np.arange(m, dtype=np.int32), np.arange(m + 1, dtype=np.int32), np.array(array[:m], dtype=np.float64)
+
+
+def csc_stack_4_by_4_ff(am, an, Ai, Ap, Ax, bm, bn, Bi, Bp, Bx, cm, cn, Ci, Cp, Cx, dm, dn, Di, Dp, Dx):
+    """[[A, B], [C, D]] -> (m, n, indices, indptr, data).  csc_numba.py:640-720 (argument order indices,
+    indptr, data; column-wise concatenation, A's entries before C's inside a column)."""
+    assert am == bm and cm == dm and an == cn and bn == dn
+
+    def half(n_, Tp, Ti, Tx, Bp_, Bi_, Bx_, off):
+        Tp, Bp_ = np.asarray(Tp, dtype=np.int64), np.asarray(Bp_, dtype=np.int64)
+        tc, bc = np.diff(Tp[:n_ + 1]), np.diff(Bp_[:n_ + 1])
+        ptr_ = np.concatenate([[0], np.cumsum(tc + bc)])
+        idx = np.empty(ptr_[-1], dtype=np.int32)
+        dat = np.empty(ptr_[-1], dtype=np.float64)
+        tcol = np.repeat(np.arange(n_), tc)
+        bcol = np.repeat(np.arange(n_), bc)
+        tpos = ptr_[tcol] + (np.arange(Tp[n_]) - Tp[tcol])
+        bpos = ptr_[bcol] + tc[bcol] + (np.arange(Bp_[n_]) - Bp_[bcol])
+        idx[tpos] = np.asarray(Ti)[:Tp[n_]]; dat[tpos] = np.asarray(Tx)[:Tp[n_]]
+        idx[bpos] = np.asarray(Bi_)[:Bp_[n_]] + off; dat[bpos] = np.asarray(Bx_)[:Bp_[n_]]
+        return ptr_, idx, dat
+
+    lp, li, lx = half(an, Ap, Ai, Ax, Cp, Ci, Cx, am)
+    rp, ri, rx = half(bn, Bp, Bi, Bx, Dp, Di, Dx, bm)
+    indptr = np.concatenate([lp, lp[-1] + rp[1:]]).astype(np.int32)
+    return am + cm, an + bn, np.concatenate([li, ri]), indptr, np.concatenate([lx, rx])
+
+
+def csc_sub_matrix_cols(Am, Anz, Ap, Ai, Ax, cols):
+    """csc_numba.py:505-537 -> (n, Bp, Bi, Bx)"""
+    cols = np.asarray(cols)
+    cnt = np.asarray(Ap)[cols + 1] - np.asarray(Ap)[cols]
+    Bp = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    src = np.concatenate([np.arange(Ap[c], Ap[c + 1]) for c in cols]) if len(cols) else np.zeros(0, dtype=np.int64)
+    src = src.astype(np.int64)
+    return int(Bp[-1]), Bp, np.asarray(Ai)[src].astype(np.int32), np.asarray(Ax)[src].astype(np.float64)
+
+
+def csc_sub_matrix(Am, Anz, Ap, Ai, Ax, rows, cols):
+    """csc_numba.py:464-502 -> (n, Bp, Bi, Bx); rows are renumbered by their position in `rows`."""
+    Bp = [0]; Bi = []; Bx = []
+    for j in cols:
+        i = 0
+        for r in rows:
+            for k in range(Ap[j], Ap[j + 1]):
+                if Ai[k] == r:
+                    Bx.append(Ax[k]); Bi.append(i); i += 1
+            if i == 0:
+                i += 1
+        Bp.append(len(Bx))
+    return len(Bx), np.array(Bp, dtype=np.int32), np.array(Bi, dtype=np.int32), np.array(Bx, dtype=np.float64)
+
+
+def csc_sub_matrix_rows(An, Anz, Ap, Ai, Ax, rows):
+    """csc_numba.py:541-578 -> (n, Bp, Bi, Bx)"""
+    return csc_sub_matrix(0, Anz, Ap, Ai, Ax, rows, range(An))
+
+
+def csc_norm(n, Ap, Ax):
+    """1-norm.  csc_numba.py:723-739"""
+    Ap = np.asarray(Ap)
+    if n == 0 or Ap[n] == 0:
+        return 0.0
+    col = np.repeat(np.arange(n), np.diff(Ap[:n + 1]))
+    return float(np.bincount(col, weights=np.abs(np.asarray(Ax)[:Ap[n]]), minlength=n).max())
+
+
+def find_islands(node_number, indptr, indices):
+    """Connected components in the reference's visiting order.  csc_numba.py:743-808."""
+    visited = np.zeros(node_number, dtype=bool)
+    islands = []
+    for node in range(node_number):
+        if visited[node]:
+            continue
+        island = []
+        stack = [node]
+        while stack:
+            v = stack.pop(0)
+            if not visited[v]:
+                visited[v] = True
+                island.append(v)
+                for i in range(indptr[v], indptr[v + 1]):
+                    k = indices[i]
+                    if not visited[k]:
+                        stack.append(k)
+        islands.append(island)
+    return islands
+
+
+def coo_to_csc(m, n, Ti, Tj, Tx, nz):
+    """csc_numba.py:331-357 -> (Cm, Cn, Cp, Ci, Cx): stable counting sort by column, duplicates kept."""
+    Tj = np.asarray(Tj)[:nz]
+    order = np.argsort(Tj, kind="stable")
+    Cp = np.concatenate([[0], np.cumsum(np.bincount(Tj, minlength=n))]).astype(np.int32)
+    return m, n, Cp, np.asarray(Ti)[:nz][order].astype(np.int32), np.asarray(Tx)[:nz][order].astype(np.float64)

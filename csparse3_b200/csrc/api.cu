@@ -1,0 +1,640 @@
+// api.cu -- extern "C" boundary of libcsparse3_b200.so (declared in include/csparse3_b200.h).
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "../../include/csparse3_b200.h"
+#include "common.cuh"
+#include "csc_kernels.cuh"
+
+namespace csp3 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char *get_error() { return g_err; }
+
+Tuning &tuning()
+{
+    static Tuning t = [] {
+        Tuning v;
+        auto env = [](const char *k) { const char *s = getenv(k); return s ? atoi(s) : 0; };
+        v.rf_S = env("CSP3_RF_S"); v.rf_warps = env("CSP3_RF_WARPS");
+        v.sv_S = env("CSP3_SV_S"); v.sv_warps = env("CSP3_SV_WARPS");
+        return v;
+    }();
+    return t;
+}
+
+namespace {
+
+int require_device()
+{
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available: libcsparse3_b200 has no CPU fallback");
+        return CSP3_ERR_CUDA;
+    }
+    return 0;
+}
+
+// RAII device buffer for the *_host entry points (synchronous semantics, default stream)
+struct Dev {
+    void *p = nullptr;
+    ~Dev() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16) == cudaSuccess ? 0 : -1; }
+    int put(const void *src, size_t bytes)
+    {
+        if (alloc(bytes)) return -1;
+        return (bytes == 0 || cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess) ? 0 : -1;
+    }
+    int get(void *dst, size_t bytes) const
+    {
+        return (bytes == 0 || cudaMemcpy(dst, p, bytes, cudaMemcpyDeviceToHost) == cudaSuccess) ? 0 : -1;
+    }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+#define CSP3_TRY(expr) do { if ((expr) != 0) { if (!*csp3::get_error()) csp3::set_error("device allocation or copy failed (%s)", cudaGetErrorString(cudaGetLastError())); return CSP3_ERR_ALLOC; } } while (0)
+
+constexpr int kMaxDevices = 16;
+
+}  // namespace
+}  // namespace csp3
+
+using namespace csp3;
+
+struct csp3_spmv_plan {
+    SpmvPlanData d;
+};
+
+struct csp3_lu_symbolic {
+    i64 n = 0, nnzA = 0;
+    std::vector<i32> Ap, Ai, q;
+    Factor F;
+    Schedule S;
+    DevSchedule dev[kMaxDevices];
+    // staging for csp3_lu_refactor_solve_host (per device, lazily created)
+    struct Stage {
+        bool ready = false;
+        i64 chunk = 0;
+        cudaStream_t st[3] = {nullptr, nullptr, nullptr};
+        double *Ax[3] = {}, *b[3] = {}, *x[3] = {}, *Lx[3] = {}, *Ux[3] = {};
+        i32 *status[3] = {};
+    } stage[kMaxDevices];
+    std::mutex mu;
+};
+
+extern "C" {
+
+int csp3_version(void) { return 100; }
+const char *csp3_last_error_string(void) { return get_error(); }
+
+int csp3_device_count(void)
+{
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return cnt;
+}
+
+int csp3_set_device(int device)
+{
+    CSP3_CUDA(cudaSetDevice(device));
+    return 0;
+}
+
+// ---- SpMV plan ------------------------------------------------------------------------------------------
+int csp3_spmv_plan_create(int64_t m, int64_t n, const int32_t *Ap_dev, const int32_t *Ai_dev, void *stream,
+                          csp3_spmv_plan **plan)
+{
+    if (!plan || m < 0 || n < 0) { set_error("spmv_plan_create: bad arguments"); return CSP3_ERR_ARG; }
+    if (int rc = require_device()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    i32 nnz = 0;
+    CSP3_CUDA(cudaMemcpyAsync(&nnz, Ap_dev + n, 4, cudaMemcpyDeviceToHost, st));
+    CSP3_CUDA(cudaStreamSynchronize(st));
+    auto *P = new csp3_spmv_plan();
+    P->d.m = m; P->d.n = n; P->d.nnz = nnz;
+    if (cudaMalloc((void **)&P->d.rp, (size_t)(m + 1) * 4) != cudaSuccess ||
+        cudaMalloc((void **)&P->d.rc, (size_t)std::max(nnz, 1) * 4) != cudaSuccess ||
+        cudaMalloc((void **)&P->d.perm, (size_t)std::max(nnz, 1) * 4) != cudaSuccess) {
+        csp3_spmv_plan_destroy(P);
+        set_error("spmv_plan_create: device allocation failed");
+        return CSP3_ERR_ALLOC;
+    }
+    int rc = transpose_device(m, n, Ap_dev, Ai_dev, nullptr, nnz, P->d.rp, P->d.rc, nullptr, P->d.perm, st);
+    if (rc) { csp3_spmv_plan_destroy(P); return rc; }
+    *plan = P;
+    return 0;
+}
+
+int csp3_spmv_plan_destroy(csp3_spmv_plan *plan)
+{
+    if (!plan) return 0;
+    cudaFree(plan->d.rp); cudaFree(plan->d.rc); cudaFree(plan->d.perm);
+    delete plan;
+    return 0;
+}
+
+int csp3_spmv_batched(const csp3_spmv_plan *plan, int64_t batch, const double *Ax, int64_t stride_ax,
+                      const double *x, double *y, double beta, void *stream)
+{
+    if (!plan) { set_error("spmv_batched: null plan"); return CSP3_ERR_ARG; }
+    return spmv_device(plan->d, batch, Ax, stride_ax, x, y, beta, (cudaStream_t)stream);
+}
+
+static int spmv_host_common(int64_t m, int64_t n, int64_t nv, const int32_t *Ap, const int32_t *Ai,
+                            const double *Ax, const double *X, double *Y, double beta)
+{
+    if (m < 0 || n < 0 || !Ap) { set_error("matvec: bad arguments"); return CSP3_ERR_ARG; }
+    if (int rc = require_device()) return rc;
+    const i64 nnz = Ap[n];
+    Dev dAp, dAi, dAx, dX, dY;
+    CSP3_TRY(dAp.put(Ap, (size_t)(n + 1) * 4));
+    CSP3_TRY(dAi.put(Ai, (size_t)nnz * 4));
+    CSP3_TRY(dAx.put(Ax, (size_t)nnz * 8));
+    CSP3_TRY(dX.put(X, (size_t)n * nv * 8));
+    if (beta != 0.0) CSP3_TRY(dY.put(Y, (size_t)m * nv * 8)); else CSP3_TRY(dY.alloc((size_t)m * nv * 8));
+    csp3_spmv_plan *P = nullptr;
+    int rc = csp3_spmv_plan_create(m, n, dAp.as<i32>(), dAi.as<i32>(), nullptr, &P);
+    if (rc) return rc;
+    if (nv == 1) rc = spmv_device(P->d, 1, dAx.as<double>(), 0, dX.as<double>(), dY.as<double>(), beta, nullptr);
+    else rc = spmm_device(P->d, nv, dAx.as<double>(), dX.as<double>(), dY.as<double>(), nullptr);
+    if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) { set_error("matvec kernel failed: %s", cudaGetErrorString(cudaGetLastError())); rc = CSP3_ERR_CUDA; }
+    csp3_spmv_plan_destroy(P);
+    if (rc) return rc;
+    CSP3_TRY(dY.get(Y, (size_t)m * nv * 8));
+    return 0;
+}
+
+int csp3_csc_mat_vec_ff_host(int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                             const double *x, double *y)
+{ return spmv_host_common(m, n, 1, Ap, Ai, Ax, x, y, 0.0); }
+
+int csp3_csc_matvec_host(int64_t n_row, int64_t n_col, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                         const double *Xx, double *Yx)
+{ return spmv_host_common(n_row, n_col, 1, Ap, Ai, Ax, Xx, Yx, 1.0); }
+
+int csp3_csc_matvecs_host(int64_t n_row, int64_t n_col, int64_t n_vecs, const int32_t *Ap, const int32_t *Ai,
+                          const double *Ax, const double *Xx, double *Yx)
+{
+    if (n_vecs == 1) return spmv_host_common(n_row, n_col, 1, Ap, Ai, Ax, Xx, Yx, 1.0);
+    return spmv_host_common(n_row, n_col, n_vecs, Ap, Ai, Ax, Xx, Yx, 1.0);
+}
+
+// ---- transposition ----------------------------------------------------------------------------------------
+int csp3_csc_transpose(int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                       int32_t *Cp, int32_t *Ci, double *Cx, void *stream)
+{
+    if (int rc = require_device()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    i32 nnz = 0;
+    CSP3_CUDA(cudaMemcpyAsync(&nnz, Ap + n, 4, cudaMemcpyDeviceToHost, st));
+    CSP3_CUDA(cudaStreamSynchronize(st));
+    return transpose_device(m, n, Ap, Ai, Ax, nnz, Cp, Ci, Cx, nullptr, st);
+}
+
+int csp3_csc_transpose_host(int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                            int32_t *Cp, int32_t *Ci, double *Cx)
+{
+    if (m < 0 || n < 0 || !Ap) { set_error("transpose: bad arguments"); return CSP3_ERR_ARG; }
+    if (int rc = require_device()) return rc;
+    const i64 nnz = Ap[n];
+    Dev dAp, dAi, dAx, dCp, dCi, dCx;
+    CSP3_TRY(dAp.put(Ap, (size_t)(n + 1) * 4));
+    CSP3_TRY(dAi.put(Ai, (size_t)nnz * 4));
+    CSP3_TRY(dAx.put(Ax, (size_t)nnz * 8));
+    CSP3_TRY(dCp.alloc((size_t)(m + 1) * 4));
+    CSP3_TRY(dCi.alloc((size_t)nnz * 4));
+    CSP3_TRY(dCx.alloc((size_t)nnz * 8));
+    int rc = transpose_device(m, n, dAp.as<i32>(), dAi.as<i32>(), dAx.as<double>(), (i32)nnz, dCp.as<i32>(),
+                              dCi.as<i32>(), dCx.as<double>(), nullptr, nullptr);
+    if (rc) return rc;
+    CSP3_CUDA(cudaDeviceSynchronize());
+    CSP3_TRY(dCp.get(Cp, (size_t)(m + 1) * 4));
+    CSP3_TRY(dCi.get(Ci, (size_t)nnz * 4));
+    CSP3_TRY(dCx.get(Cx, (size_t)nnz * 8));
+    return 0;
+}
+
+int csp3_csc_to_csr_host(int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                         int32_t *Bp, int32_t *Bi, double *Bx)
+{ return csp3_csc_transpose_host(m, n, Ap, Ai, Ax, Bp, Bi, Bx); }
+
+// ---- SpGEMM ----------------------------------------------------------------------------------------------
+int csp3_spgemm_symbolic(int64_t Am, int64_t An, const int32_t *Ap, const int32_t *Ai, int64_t Bm, int64_t Bn,
+                         const int32_t *Bp, const int32_t *Bi, int32_t *Cp, int64_t *nnz_host, void *stream)
+{
+    if (int rc = require_device()) return rc;
+    return spgemm_device(false, Am, An, Ap, Ai, nullptr, Bm, Bn, Bp, Bi, nullptr, Cp, nullptr, nullptr, nnz_host,
+                         (cudaStream_t)stream);
+}
+
+int csp3_spgemm_numeric(int64_t Am, int64_t An, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                        int64_t Bm, int64_t Bn, const int32_t *Bp, const int32_t *Bi, const double *Bx,
+                        const int32_t *Cp, int32_t *Ci, double *Cx, void *stream)
+{
+    if (int rc = require_device()) return rc;
+    return spgemm_device(true, Am, An, Ap, Ai, Ax, Bm, Bn, Bp, Bi, Bx, const_cast<i32 *>(Cp), Ci, Cx, nullptr,
+                         (cudaStream_t)stream);
+}
+
+int csp3_spgemm_symbolic_host(int64_t Am, int64_t An, const int32_t *Ap, const int32_t *Ai, int64_t Bm,
+                              int64_t Bn, const int32_t *Bp, const int32_t *Bi, int32_t *Cp, int64_t *nnz)
+{
+    if (An != Bm || !Ap || !Bp) { set_error("spgemm: bad arguments"); return CSP3_ERR_ARG; }
+    if (int rc = require_device()) return rc;
+    Dev dAp, dAi, dBp, dBi, dCp;
+    CSP3_TRY(dAp.put(Ap, (size_t)(An + 1) * 4));
+    CSP3_TRY(dAi.put(Ai, (size_t)Ap[An] * 4));
+    CSP3_TRY(dBp.put(Bp, (size_t)(Bn + 1) * 4));
+    CSP3_TRY(dBi.put(Bi, (size_t)Bp[Bn] * 4));
+    CSP3_TRY(dCp.alloc((size_t)(Bn + 1) * 4));
+    int rc = spgemm_device(false, Am, An, dAp.as<i32>(), dAi.as<i32>(), nullptr, Bm, Bn, dBp.as<i32>(),
+                           dBi.as<i32>(), nullptr, dCp.as<i32>(), nullptr, nullptr, nnz, nullptr);
+    if (rc) return rc;
+    CSP3_CUDA(cudaDeviceSynchronize());
+    CSP3_TRY(dCp.get(Cp, (size_t)(Bn + 1) * 4));
+    return 0;
+}
+
+int csp3_spgemm_numeric_host(int64_t Am, int64_t An, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                             int64_t Bm, int64_t Bn, const int32_t *Bp, const int32_t *Bi, const double *Bx,
+                             const int32_t *Cp, int32_t *Ci, double *Cx)
+{
+    if (An != Bm || !Ap || !Bp || !Cp) { set_error("spgemm: bad arguments"); return CSP3_ERR_ARG; }
+    if (int rc = require_device()) return rc;
+    const i64 nnzC = Cp[Bn];
+    Dev dAp, dAi, dAx, dBp, dBi, dBx, dCp, dCi, dCx;
+    CSP3_TRY(dAp.put(Ap, (size_t)(An + 1) * 4));
+    CSP3_TRY(dAi.put(Ai, (size_t)Ap[An] * 4));
+    CSP3_TRY(dAx.put(Ax, (size_t)Ap[An] * 8));
+    CSP3_TRY(dBp.put(Bp, (size_t)(Bn + 1) * 4));
+    CSP3_TRY(dBi.put(Bi, (size_t)Bp[Bn] * 4));
+    CSP3_TRY(dBx.put(Bx, (size_t)Bp[Bn] * 8));
+    CSP3_TRY(dCp.put(Cp, (size_t)(Bn + 1) * 4));
+    CSP3_TRY(dCi.alloc((size_t)nnzC * 4));
+    CSP3_TRY(dCx.alloc((size_t)nnzC * 8));
+    int rc = spgemm_device(true, Am, An, dAp.as<i32>(), dAi.as<i32>(), dAx.as<double>(), Bm, Bn, dBp.as<i32>(),
+                           dBi.as<i32>(), dBx.as<double>(), dCp.as<i32>(), dCi.as<i32>(), dCx.as<double>(),
+                           nullptr, nullptr);
+    if (rc) return rc;
+    CSP3_CUDA(cudaDeviceSynchronize());
+    CSP3_TRY(dCi.get(Ci, (size_t)nnzC * 4));
+    CSP3_TRY(dCx.get(Cx, (size_t)nnzC * 8));
+    return 0;
+}
+
+// ---- host symbolic ----------------------------------------------------------------------------------------
+int csp3_csc_amd(int64_t order, int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, int32_t *q)
+{
+    if (order < 0 || order > 3 || m < 0 || n < 0 || !Ap || !q) { set_error("amd: bad arguments"); return CSP3_ERR_ARG; }
+    std::vector<i32> p = amd_order(order, m, n, Ap, Ai);
+    std::memcpy(q, p.data(), (size_t)n * 4);
+    return 0;
+}
+
+int csp3_csc_etree(int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, int ata, int32_t *parent)
+{
+    if (!Ap || !parent) { set_error("etree: bad arguments"); return CSP3_ERR_ARG; }
+    std::vector<i32> p = etree(m, n, Ap, Ai, ata != 0);
+    std::memcpy(parent, p.data(), (size_t)n * 4);
+    return 0;
+}
+
+int csp3_csc_post(int64_t n, const int32_t *parent, int32_t *post)
+{
+    if (!parent || !post) { set_error("post: bad arguments"); return CSP3_ERR_ARG; }
+    std::vector<i32> p = postorder(n, parent);
+    std::memcpy(post, p.data(), (size_t)n * 4);
+    return 0;
+}
+
+int csp3_lu_analyze(int64_t order, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                    const int32_t *q_in, double tol, csp3_lu_symbolic **sym)
+{
+    if (!sym || n < 0 || !Ap || !Ai || !Ax || order < 0 || order > 3) { set_error("lu_analyze: bad arguments"); return CSP3_ERR_ARG; }
+    std::unique_ptr<csp3_lu_symbolic> Sy(new csp3_lu_symbolic());
+    Sy->n = n; Sy->nnzA = Ap[n];
+    Sy->Ap.assign(Ap, Ap + n + 1);
+    Sy->Ai.assign(Ai, Ai + Ap[n]);
+    if (q_in) Sy->q.assign(q_in, q_in + n);
+    else Sy->q = amd_order(order, n, n, Ap, Ai);
+    const int st = lu_factor(n, Ap, Ai, Ax, Sy->q.data(), tol, Sy->F);
+    if (st != 0) { set_error("lu_analyze: no non-zero pivot in step %d", st - 1); return st; }
+    const char *why = "";
+    if (!build_schedule(n, Ap, Ai, Sy->q, Sy->F, Sy->S, &why)) { set_error("lu_analyze: %s", why); return CSP3_ERR_ARG; }
+    *sym = Sy.release();
+    return 0;
+}
+
+int csp3_lu_analyze_fixed(int64_t n, const int32_t *Ap, const int32_t *Ai, const int32_t *q, const int32_t *pinv,
+                          const int32_t *Lp, const int32_t *Li, const int32_t *Up, const int32_t *Ui,
+                          csp3_lu_symbolic **sym)
+{
+    if (!sym || n < 0 || !Ap || !Ai || !pinv || !Lp || !Li || !Up || !Ui) { set_error("lu_analyze_fixed: bad arguments"); return CSP3_ERR_ARG; }
+    std::unique_ptr<csp3_lu_symbolic> Sy(new csp3_lu_symbolic());
+    Sy->n = n; Sy->nnzA = Ap[n];
+    Sy->Ap.assign(Ap, Ap + n + 1);
+    Sy->Ai.assign(Ai, Ai + Ap[n]);
+    Sy->q.resize((size_t)n);
+    for (i64 k = 0; k < n; ++k) Sy->q[k] = q ? q[k] : (i32)k;
+    Factor &F = Sy->F;
+    F.pinv.assign(pinv, pinv + n);
+    F.Lp.assign(Lp, Lp + n + 1); F.Li.assign(Li, Li + Lp[n]);
+    F.Up.assign(Up, Up + n + 1); F.Ui.assign(Ui, Ui + Up[n]);
+    F.Lx.assign((size_t)Lp[n], 0.0); F.Ux.assign((size_t)Up[n], 0.0);
+    for (i64 k = 0; k < n; ++k) {
+        if (Lp[k + 1] <= Lp[k] || Li[Lp[k]] != k || Up[k + 1] <= Up[k] || Ui[Up[k + 1] - 1] != k) {
+            set_error("lu_analyze_fixed: column %lld is not in cs_lu layout (L diagonal first, U diagonal last)", (long long)k);
+            return CSP3_ERR_ARG;
+        }
+    }
+    const char *why = "";
+    if (!build_schedule(n, Ap, Ai, Sy->q, Sy->F, Sy->S, &why)) { set_error("lu_analyze_fixed: %s", why); return CSP3_ERR_ARG; }
+    *sym = Sy.release();
+    return 0;
+}
+
+int csp3_lu_sizes(const csp3_lu_symbolic *sym, int64_t out[16])
+{
+    if (!sym || !out) { set_error("lu_sizes: bad arguments"); return CSP3_ERR_ARG; }
+    std::memset(out, 0, 16 * sizeof(int64_t));
+    out[0] = sym->n; out[1] = sym->nnzA; out[2] = (i64)sym->F.Li.size(); out[3] = (i64)sym->F.Ui.size();
+    out[4] = sym->S.lev_refactor.nlev(); out[5] = sym->S.lev_lsolve.nlev(); out[6] = sym->S.lev_usolve.nlev();
+    out[7] = sym->S.flops;
+    out[8] = (i64)(sym->S.cols.size() * sizeof(ColDesc) + sym->S.pairs.size() * sizeof(PairDesc) +
+                   sym->S.upd_map.size() * 2 + sym->S.a_src.size() * 6 +
+                   (sym->S.lrow_col.size() + sym->S.urow_col.size()) * 8 + (size_t)sym->n * 4 * 12);
+    out[9] = sym->S.max_col_len;
+    return 0;
+}
+
+int csp3_lu_get_pattern(const csp3_lu_symbolic *sym, int32_t *q, int32_t *pinv, int32_t *Lp, int32_t *Li,
+                        int32_t *Up, int32_t *Ui, double *Lx, double *Ux)
+{
+    if (!sym) { set_error("lu_get_pattern: null handle"); return CSP3_ERR_ARG; }
+    auto cp = [](void *dst, const void *src, size_t bytes) { if (dst && bytes) std::memcpy(dst, src, bytes); };
+    const Factor &F = sym->F;
+    cp(q, sym->q.data(), sym->q.size() * 4);
+    cp(pinv, F.pinv.data(), F.pinv.size() * 4);
+    cp(Lp, F.Lp.data(), F.Lp.size() * 4); cp(Li, F.Li.data(), F.Li.size() * 4);
+    cp(Up, F.Up.data(), F.Up.size() * 4); cp(Ui, F.Ui.data(), F.Ui.size() * 4);
+    cp(Lx, F.Lx.data(), F.Lx.size() * 8); cp(Ux, F.Ux.data(), F.Ux.size() * 8);
+    return 0;
+}
+
+int csp3_lu_get_levels(const csp3_lu_symbolic *sym, int kind, int32_t *level, int32_t *order, int32_t *lptr)
+{
+    if (!sym || kind < 0 || kind > 2) { set_error("lu_get_levels: bad arguments"); return CSP3_ERR_ARG; }
+    const LevelSet &L = kind == 0 ? sym->S.lev_refactor : (kind == 1 ? sym->S.lev_lsolve : sym->S.lev_usolve);
+    if (level) std::memcpy(level, L.level.data(), L.level.size() * 4);
+    if (order) std::memcpy(order, L.order.data(), L.order.size() * 4);
+    if (lptr) std::memcpy(lptr, L.lptr.data(), L.lptr.size() * 4);
+    return 0;
+}
+
+static void free_stage(csp3_lu_symbolic::Stage &g)
+{
+    for (int s = 0; s < 3; ++s) {
+        cudaFree(g.Ax[s]); cudaFree(g.b[s]); cudaFree(g.x[s]); cudaFree(g.Lx[s]); cudaFree(g.Ux[s]); cudaFree(g.status[s]);
+        if (g.st[s]) cudaStreamDestroy(g.st[s]);
+    }
+    g = csp3_lu_symbolic::Stage();
+}
+
+int csp3_lu_destroy(csp3_lu_symbolic *sym)
+{
+    if (!sym) return 0;
+    int cur = 0;
+    const bool have = cudaGetDevice(&cur) == cudaSuccess;
+    for (int d = 0; d < kMaxDevices; ++d) {
+        if (!sym->dev[d].ready && !sym->stage[d].ready) continue;
+        if (have) cudaSetDevice(d);
+        if (sym->dev[d].arena) cudaFree(sym->dev[d].arena);
+        if (sym->stage[d].ready) free_stage(sym->stage[d]);
+    }
+    if (have) cudaSetDevice(cur);
+    cudaGetLastError();
+    delete sym;
+    return 0;
+}
+
+int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
+{
+    if (!sym) { set_error("lu_upload: null handle"); return CSP3_ERR_ARG; }
+    if (int rc = require_device()) return rc;
+    int devid = 0;
+    CSP3_CUDA(cudaGetDevice(&devid));
+    if (devid >= kMaxDevices) { set_error("lu_upload: device index %d not supported", devid); return CSP3_ERR_ARG; }
+    std::lock_guard<std::mutex> lock(sym->mu);
+    DevSchedule &D = sym->dev[devid];
+    if (D.ready) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const Schedule &S = sym->S;
+    const Factor &F = sym->F;
+    struct Piece { const void *src; size_t bytes; size_t off; };
+    std::vector<Piece> pieces;
+    size_t total = 0;
+    auto add = [&](const void *src, size_t bytes) { total = (total + 255) & ~(size_t)255; pieces.push_back({src, bytes, total}); total += bytes; return pieces.size() - 1; };
+    const size_t i_cols = add(S.cols.data(), S.cols.size() * sizeof(ColDesc));
+    const size_t i_asrc = add(S.a_src.data(), S.a_src.size() * 4);
+    const size_t i_aoff = add(S.a_off.data(), S.a_off.size() * 2);
+    const size_t i_pairs = add(S.pairs.data(), S.pairs.size() * sizeof(PairDesc));
+    const size_t i_map = add(S.upd_map.data(), S.upd_map.size() * 2);
+    const size_t i_rfo = add(S.lev_refactor.order.data(), S.lev_refactor.order.size() * 4);
+    const size_t i_rfp = add(S.lev_refactor.lptr.data(), S.lev_refactor.lptr.size() * 4);
+    const size_t i_pinv = add(F.pinv.data(), F.pinv.size() * 4);
+    const size_t i_q = add(sym->q.data(), sym->q.size() * 4);
+    const size_t i_up = add(F.Up.data(), F.Up.size() * 4);
+    const size_t i_lrp = add(S.lrow_ptr.data(), S.lrow_ptr.size() * 4);
+    const size_t i_lrc = add(S.lrow_col.data(), S.lrow_col.size() * 4);
+    const size_t i_lrx = add(S.lrow_pos.data(), S.lrow_pos.size() * 4);
+    const size_t i_urp = add(S.urow_ptr.data(), S.urow_ptr.size() * 4);
+    const size_t i_urc = add(S.urow_col.data(), S.urow_col.size() * 4);
+    const size_t i_urx = add(S.urow_pos.data(), S.urow_pos.size() * 4);
+    const size_t i_lso = add(S.lev_lsolve.order.data(), S.lev_lsolve.order.size() * 4);
+    const size_t i_lsp = add(S.lev_lsolve.lptr.data(), S.lev_lsolve.lptr.size() * 4);
+    const size_t i_uso = add(S.lev_usolve.order.data(), S.lev_usolve.order.size() * 4);
+    const size_t i_usp = add(S.lev_usolve.lptr.data(), S.lev_usolve.lptr.size() * 4);
+    total = (total + 255) & ~(size_t)255;
+    char *arena = nullptr;
+    if (cudaMalloc((void **)&arena, total ? total : 256) != cudaSuccess) { set_error("lu_upload: device allocation of %zu bytes failed", total); cudaGetLastError(); return CSP3_ERR_ALLOC; }
+    for (auto &pc : pieces)
+        if (pc.bytes) CSP3_CUDA(cudaMemcpyAsync(arena + pc.off, pc.src, pc.bytes, cudaMemcpyHostToDevice, st));
+    CSP3_CUDA(cudaStreamSynchronize(st));
+    auto at = [&](size_t idx) { return (const void *)(arena + pieces[idx].off); };
+    D.arena = arena; D.arena_bytes = total;
+    D.n = (i32)sym->n; D.nnzA = (i32)sym->nnzA; D.lnz = (i32)F.Li.size(); D.unz = (i32)F.Ui.size();
+    D.max_col_len = S.max_col_len;
+    D.cols = (const int4 *)at(i_cols); D.a_src = (const i32 *)at(i_asrc); D.a_off = (const uint16_t *)at(i_aoff);
+    D.pairs = (const int4 *)at(i_pairs); D.upd_map = (const uint16_t *)at(i_map);
+    D.rf_order = (const i32 *)at(i_rfo); D.rf_lptr = (const i32 *)at(i_rfp); D.rf_nlev = (i32)S.lev_refactor.nlev();
+    D.pinv = (const i32 *)at(i_pinv); D.q = (const i32 *)at(i_q); D.Up = (const i32 *)at(i_up);
+    D.lrow_ptr = (const i32 *)at(i_lrp); D.lrow_col = (const i32 *)at(i_lrc); D.lrow_pos = (const i32 *)at(i_lrx);
+    D.urow_ptr = (const i32 *)at(i_urp); D.urow_col = (const i32 *)at(i_urc); D.urow_pos = (const i32 *)at(i_urx);
+    D.ls_order = (const i32 *)at(i_lso); D.ls_lptr = (const i32 *)at(i_lsp); D.ls_nlev = (i32)S.lev_lsolve.nlev();
+    D.us_order = (const i32 *)at(i_uso); D.us_lptr = (const i32 *)at(i_usp); D.us_nlev = (i32)S.lev_usolve.nlev();
+    D.ready = true;
+    return 0;
+}
+
+static const DevSchedule *current_schedule(const csp3_lu_symbolic *sym)
+{
+    if (!sym) { set_error("null symbolic handle"); return nullptr; }
+    int devid = 0;
+    if (cudaGetDevice(&devid) != cudaSuccess || devid >= kMaxDevices || !sym->dev[devid].ready) {
+        cudaGetLastError();
+        set_error("symbolic object not uploaded to the current device (call csp3_lu_upload)");
+        return nullptr;
+    }
+    return &sym->dev[devid];
+}
+
+int csp3_lu_refactor_batched(const csp3_lu_symbolic *sym, int64_t batch, const double *Ax, double *Lx,
+                             double *Ux, int32_t *status, void *stream)
+{
+    const DevSchedule *D = current_schedule(sym);
+    if (!D) return CSP3_ERR_ARG;
+    if (batch < 0 || !Ax || !Lx || !Ux) { set_error("lu_refactor_batched: bad arguments"); return CSP3_ERR_ARG; }
+    return launch_refactor(*D, batch, Ax, Lx, Ux, status, (cudaStream_t)stream);
+}
+
+int csp3_lu_solve_batched(const csp3_lu_symbolic *sym, int64_t batch, const double *Lx, const double *Ux,
+                          const double *b, double *x, void *stream)
+{
+    const DevSchedule *D = current_schedule(sym);
+    if (!D) return CSP3_ERR_ARG;
+    if (batch < 0 || !Lx || !Ux || !b || !x) { set_error("lu_solve_batched: bad arguments"); return CSP3_ERR_ARG; }
+    return launch_solve(*D, batch, Lx, Ux, b, x, (cudaStream_t)stream);
+}
+
+int64_t csp3_lu_workspace_bytes(const csp3_lu_symbolic *sym, int64_t batch)
+{
+    if (!sym || batch < 0) return -1;
+    return (int64_t)((sym->F.Li.size() + sym->F.Ui.size()) * 8) * batch + 512;
+}
+
+int csp3_lu_refactor_solve_batched(const csp3_lu_symbolic *sym, int64_t batch, const double *Ax,
+                                   const double *b, double *x, double *Lx, double *Ux, int32_t *status,
+                                   void *work, void *stream)
+{
+    const DevSchedule *D = current_schedule(sym);
+    if (!D) return CSP3_ERR_ARG;
+    if (batch < 0 || !Ax || !b || !x) { set_error("lu_refactor_solve_batched: bad arguments"); return CSP3_ERR_ARG; }
+    if ((!Lx || !Ux) && !work) { set_error("lu_refactor_solve_batched: Lx/Ux or work must be given"); return CSP3_ERR_ARG; }
+    char *w = (char *)(((uintptr_t)work + 255) & ~(uintptr_t)255);
+    if (!Lx) { Lx = (double *)w; w += (size_t)D->lnz * 8 * batch; }
+    if (!Ux) { Ux = (double *)w; }
+    if (int rc = launch_refactor(*D, batch, Ax, Lx, Ux, status, (cudaStream_t)stream)) return rc;
+    return launch_solve(*D, batch, Lx, Ux, b, x, (cudaStream_t)stream);
+}
+
+int csp3_lu_refactor_solve_host(csp3_lu_symbolic *sym, int64_t batch, const double *Ax, const double *b,
+                                double *x, int32_t *status)
+{
+    if (!sym || batch < 0 || !Ax || !b || !x) { set_error("lu_refactor_solve_host: bad arguments"); return CSP3_ERR_ARG; }
+    if (int rc = require_device()) return rc;
+    if (int rc = csp3_lu_upload(sym, nullptr)) return rc;
+    int devid = 0;
+    CSP3_CUDA(cudaGetDevice(&devid));
+    const DevSchedule &D = sym->dev[devid];
+    auto &G = sym->stage[devid];
+    const i64 n = D.n, nnzA = D.nnzA, lnz = D.lnz, unz = D.unz;
+    if (!G.ready) {
+        i64 chunk = (64ll << 20) / std::max<i64>(nnzA * 8, 1);
+        chunk = std::max<i64>(64, std::min<i64>(chunk, 4096));
+        chunk = (chunk + 31) & ~31ll;
+        G.chunk = chunk;
+        for (int s = 0; s < 3; ++s) {
+            CSP3_CUDA(cudaStreamCreateWithFlags(&G.st[s], cudaStreamNonBlocking));
+            CSP3_CUDA(cudaMalloc((void **)&G.Ax[s], (size_t)chunk * nnzA * 8 + 16));
+            CSP3_CUDA(cudaMalloc((void **)&G.b[s], (size_t)chunk * n * 8 + 16));
+            CSP3_CUDA(cudaMalloc((void **)&G.x[s], (size_t)chunk * n * 8 + 16));
+            CSP3_CUDA(cudaMalloc((void **)&G.Lx[s], (size_t)chunk * lnz * 8 + 16));
+            CSP3_CUDA(cudaMalloc((void **)&G.Ux[s], (size_t)chunk * unz * 8 + 16));
+            CSP3_CUDA(cudaMalloc((void **)&G.status[s], (size_t)chunk * 4 + 16));
+        }
+        G.ready = true;
+    }
+    int slot = 0;
+    for (i64 s0 = 0; s0 < batch; s0 += G.chunk, slot = (slot + 1) % 3) {
+        const i64 cnt = std::min<i64>(G.chunk, batch - s0);
+        cudaStream_t st = G.st[slot];
+        CSP3_CUDA(cudaMemcpyAsync(G.Ax[slot], Ax + s0 * nnzA, (size_t)cnt * nnzA * 8, cudaMemcpyHostToDevice, st));
+        CSP3_CUDA(cudaMemcpyAsync(G.b[slot], b + s0 * n, (size_t)cnt * n * 8, cudaMemcpyHostToDevice, st));
+        if (int rc = launch_refactor(D, cnt, G.Ax[slot], G.Lx[slot], G.Ux[slot], G.status[slot], st)) return rc;
+        if (int rc = launch_solve(D, cnt, G.Lx[slot], G.Ux[slot], G.b[slot], G.x[slot], st)) return rc;
+        CSP3_CUDA(cudaMemcpyAsync(x + s0 * n, G.x[slot], (size_t)cnt * n * 8, cudaMemcpyDeviceToHost, st));
+        if (status) CSP3_CUDA(cudaMemcpyAsync(status + s0, G.status[slot], (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < 3; ++s) CSP3_CUDA(cudaStreamSynchronize(G.st[s]));
+    return 0;
+}
+
+int csp3_lu_refactor_host(csp3_lu_symbolic *sym, int64_t batch, const double *Ax, double *Lx, double *Ux,
+                          int32_t *status)
+{
+    if (!sym || batch < 0 || !Ax || !Lx || !Ux) { set_error("lu_refactor_host: bad arguments"); return CSP3_ERR_ARG; }
+    if (int rc = require_device()) return rc;
+    if (int rc = csp3_lu_upload(sym, nullptr)) return rc;
+    const size_t nA = (size_t)sym->nnzA * batch, nL = sym->F.Li.size() * batch, nU = sym->F.Ui.size() * batch;
+    Dev dA, dL, dU, dS;
+    CSP3_TRY(dA.put(Ax, nA * 8));
+    CSP3_TRY(dL.alloc(nL * 8));
+    CSP3_TRY(dU.alloc(nU * 8));
+    CSP3_TRY(dS.alloc((size_t)batch * 4));
+    if (int rc = csp3_lu_refactor_batched(sym, batch, dA.as<double>(), dL.as<double>(), dU.as<double>(), dS.as<i32>(), nullptr)) return rc;
+    CSP3_CUDA(cudaDeviceSynchronize());
+    CSP3_TRY(dL.get(Lx, nL * 8));
+    CSP3_TRY(dU.get(Ux, nU * 8));
+    if (status) CSP3_TRY(dS.get(status, (size_t)batch * 4));
+    return 0;
+}
+
+int csp3_lu_solve_host(csp3_lu_symbolic *sym, int64_t batch, const double *Lx, const double *Ux,
+                       const double *b, double *x)
+{
+    if (!sym || batch < 0 || !Lx || !Ux || !b || !x) { set_error("lu_solve_host: bad arguments"); return CSP3_ERR_ARG; }
+    if (int rc = require_device()) return rc;
+    if (int rc = csp3_lu_upload(sym, nullptr)) return rc;
+    const size_t nL = sym->F.Li.size() * batch, nU = sym->F.Ui.size() * batch, nb = (size_t)sym->n * batch;
+    Dev dL, dU, dB, dX;
+    CSP3_TRY(dL.put(Lx, nL * 8));
+    CSP3_TRY(dU.put(Ux, nU * 8));
+    CSP3_TRY(dB.put(b, nb * 8));
+    CSP3_TRY(dX.alloc(nb * 8));
+    if (int rc = csp3_lu_solve_batched(sym, batch, dL.as<double>(), dU.as<double>(), dB.as<double>(), dX.as<double>(), nullptr)) return rc;
+    CSP3_CUDA(cudaDeviceSynchronize());
+    CSP3_TRY(dX.get(x, nb * 8));
+    return 0;
+}
+
+int csp3_csc_lusol_host(int64_t order, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                        double *b, double tol)
+{
+    if (int rc = require_device()) return rc;
+    csp3_lu_symbolic *sym = nullptr;
+    int rc = csp3_lu_analyze(order, n, Ap, Ai, Ax, nullptr, tol, &sym);
+    if (rc) return rc;
+    std::vector<double> x((size_t)std::max<i64>(n, 1));
+    i32 status = 0;
+    rc = csp3_lu_refactor_solve_host(sym, 1, Ax, b, x.data(), &status);
+    csp3_lu_destroy(sym);
+    if (rc) return rc;
+    if (status) { set_error("lusol: zero or non-finite pivot in column %d", status - 1); return status; }
+    std::memcpy(b, x.data(), (size_t)n * 8);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,375 @@
+// csc_kernels.cu -- CSC transposition / CSC->CSR, SpMV, SpMM and hash SpGEMM for sm_100a.
+//
+// Reference semantics (cited per kernel): src/CSparse3/csc_numba.py and src/sparsetools/csc.h, csr.h.
+// All kernels are deterministic: no floating-point atomics on a contended address, so results do not depend
+// on grid shape or on how a batch is sharded across GPUs.
+#include "csc_kernels.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace csp3 {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ int column_of(const i32 *__restrict__ Ap, int n, int p)
+{
+    // largest c with Ap[c] <= p  (empty columns are skipped because Ap[c+1] > p is required)
+    int lo = 0, hi = n;                       // invariant: Ap[lo] <= p < Ap[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(Ap + mid) <= p) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ---- counting sort: histogram -> scan -> bucket fill -> per-row rank sort ---------------------------------
+__global__ void k_row_hist(int nnz, const i32 *__restrict__ Ai, i32 *cnt)
+{
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += gridDim.x * blockDim.x)
+        atomicAdd(cnt + __ldg(Ai + p), 1);
+}
+
+// single-CTA exclusive scan of cnt[0..m) into ptr[0..m]; cnt is overwritten with the running cursor (= ptr)
+__global__ void k_scan(int m, i32 *cnt, i32 *ptr)
+{
+    __shared__ i32 warp_sum[32];
+    __shared__ i32 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int base = 0; base < m; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const i32 v = (i < m) ? cnt[i] : 0;
+        i32 s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const i32 t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        if (lane == 31) warp_sum[warp] = s;
+        __syncthreads();
+        if (warp == 0) {
+            i32 ws = (lane < nw) ? warp_sum[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const i32 t = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += t;
+            }
+            warp_sum[lane] = ws;
+        }
+        __syncthreads();
+        const i32 excl = carry + (warp ? warp_sum[warp - 1] : 0) + s - v;
+        if (i < m) { ptr[i] = excl; cnt[i] = excl; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ptr[m] = carry;
+}
+
+__global__ void k_bucket_fill(int nnz, const i32 *__restrict__ Ai, i32 *cursor, i32 *bucket)
+{
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += gridDim.x * blockDim.x)
+        bucket[atomicAdd(cursor + __ldg(Ai + p), 1)] = p;
+}
+
+// One warp per row: sort the row's source-entry ids ascending (== ascending column, stable inside a column:
+// exactly the order the sequential counting sort of csc_to_csr / csc_transpose produces), then emit.
+__global__ void k_row_emit(int m, int n, const i32 *__restrict__ Ap, const double *__restrict__ Ax,
+                           const i32 *__restrict__ ptr, const i32 *__restrict__ bucket, i32 *perm, i32 *Ci,
+                           double *Cx)
+{
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < m; r += gridDim.x * wpb) {
+        const int beg = __ldg(ptr + r), len = __ldg(ptr + r + 1) - beg;
+        for (int t = lane; t < len; t += 32) {
+            const int p = __ldg(bucket + beg + t);
+            int rank = 0;
+            for (int u = 0; u < len; ++u) rank += (__ldg(bucket + beg + u) < p);
+            if (perm) perm[beg + rank] = p;
+            if (Ci) Ci[beg + rank] = column_of(Ap, n, p);
+            if (Cx) Cx[beg + rank] = __ldg(Ax + p);
+        }
+    }
+}
+
+// ---- SpMV / SpMM (row gather over the CSR view; values stay in the caller's CSC order) --------------------
+// y[b][r] = beta*y[b][r] + sum_t Ax[b][perm[t]] * x[b][col[t]]     G lanes per row, batch on blockIdx.y
+template <int G>
+__global__ void k_spmv(int m, int n, i64 nnz_stride, const i32 *__restrict__ rp, const i32 *__restrict__ rc,
+                       const i32 *__restrict__ perm, const double *__restrict__ Ax, const double *__restrict__ x,
+                       double *y, double beta)
+{
+    const i64 b = blockIdx.y;
+    const double *Axb = Ax + b * nnz_stride;
+    const double *xb = x + b * n;
+    double *yb = y + b * m;
+    const int sub = threadIdx.x % G;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) / G; r < m; r += gridDim.x * blockDim.x / G) {
+        const int beg = __ldg(rp + r), end = __ldg(rp + r + 1);
+        double s = 0.0;
+        for (int t = beg + sub; t < end; t += G)
+            s += __ldg(Axb + __ldg(perm + t)) * __ldg(xb + __ldg(rc + t));
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (sub == 0) yb[r] = (beta == 0.0) ? s : beta * yb[r] + s;
+    }
+}
+
+// Y[r][v] += sum_t Ax[perm[t]] * X[col[t]][v]   (row-major X, Y; thread per (r, v)), sparsetools csc.h:68-84
+__global__ void k_spmm(int m, int nv, const i32 *__restrict__ rp, const i32 *__restrict__ rc,
+                       const i32 *__restrict__ perm, const double *__restrict__ Ax, const double *__restrict__ X,
+                       double *Y)
+{
+    const i64 total = (i64)m * nv;
+    for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / nv), v = (int)(idx - (i64)r * nv);
+        const int beg = __ldg(rp + r), end = __ldg(rp + r + 1);
+        double s = Y[idx];
+        for (int t = beg; t < end; ++t) s += __ldg(Ax + __ldg(perm + t)) * __ldg(X + (i64)__ldg(rc + t) * nv + v);
+        Y[idx] = s;
+    }
+}
+
+// ---- SpGEMM (hash accumulation per output column) -----------------------------------------------------------
+__global__ void k_spgemm_ub(int Bn, const i32 *__restrict__ Ap, const i32 *__restrict__ Bp,
+                            const i32 *__restrict__ Bi, i32 *ub)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < Bn; j += gridDim.x * blockDim.x) {
+        i64 s = 0;
+        for (int pb = __ldg(Bp + j); pb < __ldg(Bp + j + 1); ++pb) {
+            const int k = __ldg(Bi + pb);
+            s += __ldg(Ap + k + 1) - __ldg(Ap + k);
+        }
+        ub[j] = (i32)min(s, (i64)INT32_MAX);
+    }
+}
+
+__device__ __forceinline__ unsigned hash_row(int r, unsigned mask) { return ((unsigned)r * 2654435761u >> 7) & mask; }
+
+// insert key; returns slot.  *fresh = true when this call created the entry.
+__device__ __forceinline__ int hash_insert(i32 *keys, unsigned mask, int row, bool *fresh)
+{
+    unsigned h = hash_row(row, mask);
+    for (;;) {
+        const i32 prev = atomicCAS(keys + h, -1, row);
+        if (prev == -1) { *fresh = true; return (int)h; }
+        if (prev == row) { *fresh = false; return (int)h; }
+        h = (h + 1) & mask;
+    }
+}
+
+constexpr int kSmallSlots = 1024;     // per-warp table for columns with <= 512 candidate products
+constexpr int kSmallWarps = 4;
+
+// Process one output column with `nthr` cooperating threads (a warp with a shared-memory table, or a whole
+// CTA with a global-memory table).  Products are visited pb-sequentially and pa-parallel, so inside a step
+// all target rows are distinct (A has no duplicate row inside a column) and the per-row summation order is
+// the reference's loop order (csc_numba.py:284-293).
+template <bool NUMERIC, bool BLOCK>
+__device__ void spgemm_column(int j, int tid, int nthr, const i32 *__restrict__ Ap, const i32 *__restrict__ Ai,
+                              const double *__restrict__ Ax, const i32 *__restrict__ Bp,
+                              const i32 *__restrict__ Bi, const double *__restrict__ Bx, i32 *keys, double *vals,
+                              unsigned mask, i32 *count_out, const i32 *__restrict__ Cp, i32 *Ci, double *Cx)
+{
+    const int slots = (int)mask + 1;
+    for (int s = tid; s < slots; s += nthr) { keys[s] = -1; if (NUMERIC) vals[s] = 0.0; }
+    if (BLOCK) __syncthreads(); else __syncwarp();
+    int fresh_cnt = 0;
+    for (int pb = __ldg(Bp + j); pb < __ldg(Bp + j + 1); ++pb) {
+        const int k = __ldg(Bi + pb);
+        const double bv = NUMERIC ? __ldg(Bx + pb) : 0.0;
+        for (int pa = __ldg(Ap + k) + tid; pa < __ldg(Ap + k + 1); pa += nthr) {
+            bool fresh;
+            const int slot = hash_insert(keys, mask, __ldg(Ai + pa), &fresh);
+            fresh_cnt += fresh;
+            if (NUMERIC) atomicAdd(vals + slot, __dmul_rn(bv, __ldg(Ax + pa)));
+        }
+        if (BLOCK) __syncthreads(); else __syncwarp();
+    }
+    if (!NUMERIC) {
+        if (fresh_cnt) atomicAdd(count_out + j, fresh_cnt);
+        return;
+    }
+    // emit sorted by row: rank of each occupied slot among the occupied slots
+    const int base = __ldg(Cp + j);
+    for (int s = tid; s < slots; s += nthr) {
+        const int row = keys[s];
+        if (row < 0) continue;
+        int rank = 0;
+        for (int u = 0; u < slots; ++u) { const int o = keys[u]; rank += (o >= 0 && o < row); }
+        Ci[base + rank] = row;
+        Cx[base + rank] = vals[s];
+    }
+    if (BLOCK) __syncthreads(); else __syncwarp();
+}
+
+template <bool NUMERIC>
+__global__ void __launch_bounds__(kSmallWarps * 32)
+k_spgemm_small(int ncols, const i32 *__restrict__ list, const i32 *__restrict__ Ap, const i32 *__restrict__ Ai,
+               const double *__restrict__ Ax, const i32 *__restrict__ Bp, const i32 *__restrict__ Bi,
+               const double *__restrict__ Bx, const i32 *__restrict__ slots_of, i32 *count_out,
+               const i32 *__restrict__ Cp, i32 *Ci, double *Cx)
+{
+    __shared__ i32 s_keys[kSmallWarps][kSmallSlots];
+    __shared__ double s_vals[NUMERIC ? kSmallWarps : 1][NUMERIC ? kSmallSlots : 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = blockIdx.x * kSmallWarps + warp; c < ncols; c += gridDim.x * kSmallWarps) {
+        const int j = __ldg(list + c);
+        const unsigned mask = (unsigned)__ldg(slots_of + c) - 1u;
+        spgemm_column<NUMERIC, false>(j, lane, 32, Ap, Ai, Ax, Bp, Bi, Bx, s_keys[warp],
+                                      NUMERIC ? (double *)s_vals[warp] : (double *)nullptr, mask, count_out, Cp, Ci, Cx);
+    }
+}
+
+template <bool NUMERIC>
+__global__ void __launch_bounds__(kThreads)
+k_spgemm_big(int ncols, const i32 *__restrict__ list, const i32 *__restrict__ Ap, const i32 *__restrict__ Ai,
+             const double *__restrict__ Ax, const i32 *__restrict__ Bp, const i32 *__restrict__ Bi,
+             const double *__restrict__ Bx, const i32 *__restrict__ slots_of, const i64 *__restrict__ tab_off,
+             i32 *tab_keys, double *tab_vals, i32 *count_out, const i32 *__restrict__ Cp, i32 *Ci, double *Cx)
+{
+    for (int c = blockIdx.x; c < ncols; c += gridDim.x) {
+        const int j = __ldg(list + c);
+        const unsigned mask = (unsigned)__ldg(slots_of + c) - 1u;
+        const i64 off = tab_off[c];
+        spgemm_column<NUMERIC, true>(j, threadIdx.x, blockDim.x, Ap, Ai, Ax, Bp, Bi, Bx, tab_keys + off,
+                                     NUMERIC ? tab_vals + off : nullptr, mask, count_out, Cp, Ci, Cx);
+    }
+}
+
+inline int grid_for(i64 work, int per_block, int cap = kNumSMs * 16)
+{
+    const i64 g = (work + per_block - 1) / per_block;
+    return (int)std::max<i64>(1, std::min<i64>(g, cap));
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    cudaStream_t st;
+    explicit DevBuf(cudaStream_t s) : st(s) {}
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    int alloc(size_t bytes) { return cudaMallocAsync(&p, std::max<size_t>(bytes, 16), st) == cudaSuccess ? 0 : -1; }
+    template <class T> T *as() { return (T *)p; }
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+int transpose_device(i64 m, i64 n, const i32 *Ap, const i32 *Ai, const double *Ax, i32 nnz, i32 *Cp, i32 *Ci,
+                     double *Cx, i32 *perm, cudaStream_t st)
+{
+    DevBuf cursor(st), bucket(st);
+    if (cursor.alloc((size_t)(m + 1) * 4) || bucket.alloc((size_t)nnz * 4)) { set_error("device alloc failed"); return -3; }
+    CSP3_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)(m + 1) * 4, st));
+    if (nnz > 0) k_row_hist<<<grid_for(nnz, kThreads), kThreads, 0, st>>>(nnz, Ai, cursor.as<i32>());
+    k_scan<<<1, 1024, 0, st>>>((int)m, cursor.as<i32>(), Cp);
+    if (nnz > 0) {
+        k_bucket_fill<<<grid_for(nnz, kThreads), kThreads, 0, st>>>(nnz, Ai, cursor.as<i32>(), bucket.as<i32>());
+        k_row_emit<<<grid_for(m, kThreads / 32), kThreads, 0, st>>>((int)m, (int)n, Ap, Ax, Cp, bucket.as<i32>(),
+                                                                     perm, Ci, Cx);
+    }
+    CSP3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int spmv_device(const SpmvPlanData &P, i64 batch, const double *Ax, i64 stride_ax, const double *x, double *y,
+                double beta, cudaStream_t st)
+{
+    if (batch <= 0 || P.m == 0) return 0;
+    const i64 rows_per_block = kThreads / 4;
+    i64 gx = (P.m + rows_per_block - 1) / rows_per_block;
+    gx = std::max<i64>(1, std::min<i64>(gx, 65535 * 16));
+    for (i64 b0 = 0; b0 < batch; b0 += 65535) {
+        const i64 nb = std::min<i64>(65535, batch - b0);
+        dim3 grid((unsigned)gx, (unsigned)nb);
+        k_spmv<4><<<grid, kThreads, 0, st>>>((int)P.m, (int)P.n, stride_ax, P.rp, P.rc, P.perm, Ax + b0 * stride_ax,
+                                             x + b0 * P.n, y + b0 * P.m, beta);
+    }
+    CSP3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int spmm_device(const SpmvPlanData &P, i64 nv, const double *Ax, const double *X, double *Y, cudaStream_t st)
+{
+    if (P.m == 0 || nv == 0) return 0;
+    k_spmm<<<grid_for(P.m * nv, kThreads), kThreads, 0, st>>>((int)P.m, (int)nv, P.rp, P.rc, P.perm, Ax, X, Y);
+    CSP3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Host-orchestrated SpGEMM phase.  numeric == false: fills Cp (exclusive scan of per-column distinct-row counts)
+// and *nnz_out.  numeric == true: fills Ci (sorted inside columns) and Cx using Cp.
+int spgemm_device(bool numeric, i64 Am, i64 An, const i32 *Ap, const i32 *Ai, const double *Ax, i64 Bm, i64 Bn,
+                  const i32 *Bp, const i32 *Bi, const double *Bx, i32 *Cp, i32 *Ci, double *Cx, i64 *nnz_out,
+                  cudaStream_t st)
+{
+    if (An != Bm) { set_error("spgemm: inner dimensions differ (%lld vs %lld)", (long long)An, (long long)Bm); return -1; }
+    if (Bn == 0) { if (!numeric) { CSP3_CUDA(cudaMemsetAsync(Cp, 0, 4, st)); if (nnz_out) *nnz_out = 0; } return 0; }
+    DevBuf ub(st);
+    if (ub.alloc((size_t)Bn * 4)) { set_error("device alloc failed"); return -3; }
+    k_spgemm_ub<<<grid_for(Bn, kThreads), kThreads, 0, st>>>((int)Bn, Ap, Bp, Bi, ub.as<i32>());
+    std::vector<i32> h_ub((size_t)Bn);
+    CSP3_CUDA(cudaMemcpyAsync(h_ub.data(), ub.p, (size_t)Bn * 4, cudaMemcpyDeviceToHost, st));
+    CSP3_CUDA(cudaStreamSynchronize(st));
+    // partition columns by candidate-product count
+    std::vector<i32> small_list, small_slots, big_list, big_slots;
+    std::vector<i64> big_off;
+    i64 tab_total = 0;
+    for (i64 j = 0; j < Bn; ++j) {
+        const i64 cand = std::min<i64>(h_ub[j], Am);
+        if (cand == 0) continue;
+        i64 slots = 32;
+        while (slots < 2 * cand) slots <<= 1;
+        if (slots <= kSmallSlots) { small_list.push_back((i32)j); small_slots.push_back((i32)slots); }
+        else { big_list.push_back((i32)j); big_slots.push_back((i32)slots); big_off.push_back(tab_total); tab_total += slots; }
+    }
+    DevBuf d_small(st), d_small_slots(st), d_big(st), d_big_slots(st), d_big_off(st), tkeys(st), tvals(st), cnt(st);
+    auto upload = [&](DevBuf &d, const void *src, size_t bytes) -> int {
+        if (d.alloc(bytes)) return -3;
+        if (bytes) return cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, st) == cudaSuccess ? 0 : -2;
+        return 0;
+    };
+    if (upload(d_small, small_list.data(), small_list.size() * 4) || upload(d_small_slots, small_slots.data(), small_slots.size() * 4) ||
+        upload(d_big, big_list.data(), big_list.size() * 4) || upload(d_big_slots, big_slots.data(), big_slots.size() * 4) ||
+        upload(d_big_off, big_off.data(), big_off.size() * 8) || tkeys.alloc((size_t)tab_total * 4) ||
+        (numeric && tvals.alloc((size_t)tab_total * 8))) { set_error("spgemm: device alloc/copy failed"); return -3; }
+    i32 *count = nullptr;
+    if (!numeric) {
+        if (cnt.alloc((size_t)(Bn + 1) * 4)) { set_error("device alloc failed"); return -3; }
+        CSP3_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)(Bn + 1) * 4, st));
+        count = cnt.as<i32>();
+    }
+    const int ns = (int)small_list.size(), nb = (int)big_list.size();
+    if (ns) {
+        const int g = grid_for(ns, kSmallWarps, kNumSMs * 8);
+        if (numeric) k_spgemm_small<true><<<g, kSmallWarps * 32, 0, st>>>(ns, d_small.as<i32>(), Ap, Ai, Ax, Bp, Bi, Bx, d_small_slots.as<i32>(), nullptr, Cp, Ci, Cx);
+        else k_spgemm_small<false><<<g, kSmallWarps * 32, 0, st>>>(ns, d_small.as<i32>(), Ap, Ai, Ax, Bp, Bi, Bx, d_small_slots.as<i32>(), count, nullptr, nullptr, nullptr);
+    }
+    if (nb) {
+        const int g = std::min(nb, kNumSMs * 4);
+        if (numeric) k_spgemm_big<true><<<g, kThreads, 0, st>>>(nb, d_big.as<i32>(), Ap, Ai, Ax, Bp, Bi, Bx, d_big_slots.as<i32>(), d_big_off.as<i64>(), tkeys.as<i32>(), tvals.as<double>(), nullptr, Cp, Ci, Cx);
+        else k_spgemm_big<false><<<g, kThreads, 0, st>>>(nb, d_big.as<i32>(), Ap, Ai, Ax, Bp, Bi, Bx, d_big_slots.as<i32>(), d_big_off.as<i64>(), tkeys.as<i32>(), nullptr, count, nullptr, nullptr, nullptr);
+    }
+    CSP3_CUDA(cudaGetLastError());
+    if (!numeric) {
+        // Cp = exclusive scan of counts; overflow check on the host (sparsetools csr.h:591-596)
+        std::vector<i32> h_cnt((size_t)Bn);
+        CSP3_CUDA(cudaMemcpyAsync(h_cnt.data(), cnt.p, (size_t)Bn * 4, cudaMemcpyDeviceToHost, st));
+        CSP3_CUDA(cudaStreamSynchronize(st));
+        std::vector<i32> h_cp((size_t)Bn + 1);
+        i64 run = 0;
+        for (i64 j = 0; j < Bn; ++j) { h_cp[j] = (i32)run; run += h_cnt[j]; if (run > INT32_MAX) { set_error("nnz of the result is too large"); return -4; } }
+        h_cp[Bn] = (i32)run;
+        CSP3_CUDA(cudaMemcpyAsync(Cp, h_cp.data(), (size_t)(Bn + 1) * 4, cudaMemcpyHostToDevice, st));
+        CSP3_CUDA(cudaStreamSynchronize(st));
+        if (nnz_out) *nnz_out = run;
+    }
+    return 0;
+}
+
+}  // namespace csp3

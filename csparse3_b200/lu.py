@@ -1,0 +1,180 @@
+"""Batched sparse LU on one pattern: symbolic phase cached on the host, numeric phase on the GPU.
+
+No reference counterpart.  `LuSymbolic` owns the opaque csp3_lu_symbolic handle of
+include/csparse3_b200.h; torch tensors are only the carriers of device buffers (data_ptr + current stream).
+
+    sym = LuSymbolic(n, Ap, Ai, Ax0, order=1, tol=1e-3)      # AMD + first pivoted LU on the host, once
+    x, status = sym.refactor_solve(Ax_dev, b_dev)             # every later system: CUDA only
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import as_f64, as_i32, check, ptr
+
+DEFAULT_ORDER = 1      # amd(A + A'): power-flow Jacobians are structurally symmetric
+DEFAULT_TOL = 1e-3     # threshold partial pivoting with diagonal preference (CSparse cs_lu `tol`)
+
+
+class LuSymbolic:
+    def __init__(self, n, Ap, Ai, Ax, order=DEFAULT_ORDER, tol=DEFAULT_TOL, q=None):
+        Ap, Ai, Ax = as_i32(Ap, "Ap"), as_i32(Ai, "Ai"), as_f64(Ax, "Ax")
+        qa = None if q is None else as_i32(q, "q")
+        h = C.c_void_p()
+        check(_lib.lib().csp3_lu_analyze(order, n, ptr(Ap), ptr(Ai), ptr(Ax), ptr(qa), float(tol), C.byref(h)),
+              "csp3_lu_analyze")
+        self._init_from_handle(h, n)
+
+    @classmethod
+    def from_pattern(cls, n, Ap, Ai, q, pinv, Lp, Li, Up, Ui):
+        """Rebuild the object from a cached ordering / pivot sequence / pattern (no factorisation)."""
+        self = cls.__new__(cls)
+        arrs = [as_i32(a) for a in (Ap, Ai)] + [None if q is None else as_i32(q)] + \
+               [as_i32(a) for a in (pinv, Lp, Li, Up, Ui)]
+        h = C.c_void_p()
+        check(_lib.lib().csp3_lu_analyze_fixed(n, *[ptr(a) for a in arrs], C.byref(h)), "csp3_lu_analyze_fixed")
+        self._init_from_handle(h, n)
+        return self
+
+    def _init_from_handle(self, h, n):
+        self._h = h
+        L = _lib.lib()
+        sz = (C.c_int64 * 16)()
+        check(L.csp3_lu_sizes(h, C.byref(sz)), "csp3_lu_sizes")
+        self.n, self.nnz, self.lnz, self.unz = int(sz[0]), int(sz[1]), int(sz[2]), int(sz[3])
+        self.nlev_refactor, self.nlev_lsolve, self.nlev_usolve = int(sz[4]), int(sz[5]), int(sz[6])
+        self.flops, self.schedule_bytes, self.max_col_len = int(sz[7]), int(sz[8]), int(sz[9])
+        n = self.n
+        self.q = np.empty(n, dtype=np.int32); self.pinv = np.empty(n, dtype=np.int32)
+        self.Lp = np.empty(n + 1, dtype=np.int32); self.Li = np.empty(self.lnz, dtype=np.int32)
+        self.Up = np.empty(n + 1, dtype=np.int32); self.Ui = np.empty(self.unz, dtype=np.int32)
+        self.Lx0 = np.empty(self.lnz, dtype=np.float64); self.Ux0 = np.empty(self.unz, dtype=np.float64)
+        check(L.csp3_lu_get_pattern(h, ptr(self.q), ptr(self.pinv), ptr(self.Lp), ptr(self.Li), ptr(self.Up),
+                                    ptr(self.Ui), ptr(self.Lx0), ptr(self.Ux0)), "csp3_lu_get_pattern")
+        self._uploaded = set()
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                _lib.lib().csp3_lu_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    @property
+    def nnz_lu(self):
+        """nnz(L + U) counting the diagonal once."""
+        return self.lnz + self.unz - self.n
+
+    def bytes_per_system(self, fused=False):
+        """Algorithmic HBM bytes of one refactor+solve."""
+        if fused:
+            return 8 * self.nnz + 8 * self.nnz_lu + 16 * self.n
+        return 8 * self.nnz + 16 * self.nnz_lu + 16 * self.n
+
+    def levels(self, kind):
+        """kind 0 refactor, 1 L-solve, 2 U-solve -> (level[n], order[n], lptr[nlev+1])"""
+        nlev = (self.nlev_refactor, self.nlev_lsolve, self.nlev_usolve)[kind]
+        level = np.empty(self.n, dtype=np.int32)
+        order = np.empty(self.n, dtype=np.int32)
+        lptr = np.empty(nlev + 1, dtype=np.int32)
+        check(_lib.lib().csp3_lu_get_levels(self._h, kind, ptr(level), ptr(order), ptr(lptr)), "csp3_lu_get_levels")
+        return level, order, lptr
+
+    # ---- host-buffer calls (numpy in, numpy out) ------------------------------------------------------------
+    def refactor_host(self, Ax):
+        Ax = np.ascontiguousarray(Ax, dtype=np.float64).reshape(-1, self.nnz)
+        B = Ax.shape[0]
+        Lx = np.empty((B, self.lnz)); Ux = np.empty((B, self.unz)); status = np.zeros(B, dtype=np.int32)
+        check(_lib.lib().csp3_lu_refactor_host(self._h, B, ptr(Ax), ptr(Lx), ptr(Ux), ptr(status)), "csp3_lu_refactor_host")
+        return Lx, Ux, status
+
+    def solve_host(self, Lx, Ux, b):
+        Lx = np.ascontiguousarray(Lx, dtype=np.float64).reshape(-1, self.lnz)
+        Ux = np.ascontiguousarray(Ux, dtype=np.float64).reshape(-1, self.unz)
+        b = np.ascontiguousarray(b, dtype=np.float64).reshape(-1, self.n)
+        x = np.empty_like(b)
+        check(_lib.lib().csp3_lu_solve_host(self._h, b.shape[0], ptr(Lx), ptr(Ux), ptr(b), ptr(x)), "csp3_lu_solve_host")
+        return x
+
+    def refactor_solve_host(self, Ax, b, x=None, status=None):
+        """End-to-end batched call on HOST buffers (numpy arrays or pinned torch CPU tensors viewed as numpy):
+        chunked H2D -> refactor -> solve -> D2H pipeline inside the library."""
+        B = Ax.shape[0]
+        assert Ax.dtype == np.float64 and b.dtype == np.float64 and Ax.flags.c_contiguous and b.flags.c_contiguous
+        if x is None:
+            x = np.empty((B, self.n), dtype=np.float64)
+        if status is None:
+            status = np.zeros(B, dtype=np.int32)
+        check(_lib.lib().csp3_lu_refactor_solve_host(self._h, B, ptr(Ax), ptr(b), ptr(x), ptr(status)),
+              "csp3_lu_refactor_solve_host")
+        return x, status
+
+    # ---- device calls (torch CUDA tensors carry the buffers) ------------------------------------------------
+    def _upload(self, dev_index, stream):
+        if dev_index not in self._uploaded:
+            check(_lib.lib().csp3_lu_upload(self._h, stream), "csp3_lu_upload")
+            self._uploaded.add(dev_index)
+
+    @staticmethod
+    def _dev(t, shape_last, name):
+        import torch
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+            raise TypeError("%s must be a contiguous float64 CUDA tensor" % name)
+        if t.shape[-1] != shape_last:
+            raise ValueError("%s: last dimension must be %d" % (name, shape_last))
+        return t
+
+    def refactor(self, Ax, Lx=None, Ux=None, status=None):
+        import torch
+        Ax = self._dev(Ax, self.nnz, "Ax")
+        B = Ax.numel() // self.nnz
+        with torch.cuda.device(Ax.device):
+            st = torch.cuda.current_stream().cuda_stream
+            self._upload(Ax.device.index, st)
+            Lx = torch.empty((B, self.lnz), dtype=torch.float64, device=Ax.device) if Lx is None else Lx
+            Ux = torch.empty((B, self.unz), dtype=torch.float64, device=Ax.device) if Ux is None else Ux
+            status = torch.empty(B, dtype=torch.int32, device=Ax.device) if status is None else status
+            check(_lib.lib().csp3_lu_refactor_batched(self._h, B, Ax.data_ptr(), Lx.data_ptr(), Ux.data_ptr(),
+                                                      status.data_ptr(), st), "csp3_lu_refactor_batched")
+        return Lx, Ux, status
+
+    def solve(self, Lx, Ux, b, x=None):
+        import torch
+        b = self._dev(b, self.n, "b")
+        B = b.numel() // self.n
+        with torch.cuda.device(b.device):
+            st = torch.cuda.current_stream().cuda_stream
+            self._upload(b.device.index, st)
+            x = torch.empty_like(b) if x is None else x
+            check(_lib.lib().csp3_lu_solve_batched(self._h, B, self._dev(Lx, self.lnz, "Lx").data_ptr(),
+                                                   self._dev(Ux, self.unz, "Ux").data_ptr(), b.data_ptr(),
+                                                   x.data_ptr(), st), "csp3_lu_solve_batched")
+        return x
+
+    def refactor_solve(self, Ax, b, x=None, Lx=None, Ux=None, status=None, work=None):
+        """x = A_k \\ b_k for every system of the batch (device tensors).  Factors are kept only if Lx/Ux are
+        given; otherwise they live in `work` (allocated here if None)."""
+        import torch
+        Ax = self._dev(Ax, self.nnz, "Ax")
+        b = self._dev(b, self.n, "b")
+        B = b.numel() // self.n
+        with torch.cuda.device(b.device):
+            st = torch.cuda.current_stream().cuda_stream
+            self._upload(b.device.index, st)
+            x = torch.empty_like(b) if x is None else x
+            status = torch.empty(B, dtype=torch.int32, device=b.device) if status is None else status
+            if (Lx is None or Ux is None) and work is None:
+                nbytes = _lib.lib().csp3_lu_workspace_bytes(self._h, B)
+                work = torch.empty(nbytes, dtype=torch.uint8, device=b.device)
+            check(_lib.lib().csp3_lu_refactor_solve_batched(
+                self._h, B, Ax.data_ptr(), b.data_ptr(), x.data_ptr(),
+                None if Lx is None else Lx.data_ptr(), None if Ux is None else Ux.data_ptr(),
+                status.data_ptr(), None if work is None else work.data_ptr(), st), "csp3_lu_refactor_solve_batched")
+        return x, status
+
+    def workspace(self, batch, device):
+        import torch
+        return torch.empty(_lib.lib().csp3_lu_workspace_bytes(self._h, batch), dtype=torch.uint8, device=device)

@@ -1,0 +1,169 @@
+/*
+ * csparse3_b200.h -- C ABI of libcsparse3_b200.so, the B200 (sm_100a) drop-in for the numeric hot
+ * path of SanPen/CSparse3.
+ *
+ * Every entry point replaces one flat kernel of the reference's backend seam
+ *     src/CSparse3/csc.py:33-41   (sptools.* and `from CSparse3.csc_numba import *`)
+ * and is cited against it below.  LU / triangular solve / ordering entry points have no reference
+ * counterpart (the reference ships none); they follow the flat signatures SURVEY.md
+ * section 8(a11) proposes in the reference's idiom and the semantics of upstream CSparse (cs_amd, cs_lu,
+ * cs_lsolve, cs_usolve, cs_ipvec).
+ *
+ * Conventions
+ *   - indices int32_t, values double, sizes int64_t (reference: i4[:] / f8[:] / i8, csc_numba.py:36-744).
+ *   - `_host` suffix: all array arguments are HOST pointers; the call copies in, runs the CUDA kernels and
+ *     copies out before returning (this is what the numpy-facing drop-in module binds).
+ *   - no suffix: all array arguments are DEVICE pointers, the call is stream-ordered on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream), never synchronises and never retains
+ *     caller pointers.  The caller owns every buffer.
+ *   - return value: 0 ok; negative = argument / CUDA error (text in csp3_last_error_string());
+ *     positive k = zero or non-finite pivot at column k-1 (KLU style) where documented.
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns CSP3_ERR_CUDA.
+ */
+#ifndef CSPARSE3_B200_H
+#define CSPARSE3_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSP3_OK 0
+#define CSP3_ERR_ARG (-1)
+#define CSP3_ERR_CUDA (-2)
+#define CSP3_ERR_ALLOC (-3)
+#define CSP3_ERR_OVERFLOW (-4) /* nnz of a product exceeds int32 (sparsetools csr.h:591-596) */
+#define CSP3_ERR_SINGULAR (-5)
+
+/* ---- library ------------------------------------------------------------------------------------- */
+int csp3_version(void);
+const char *csp3_last_error_string(void);
+int csp3_device_count(void);             /* 0 when no CUDA device is usable */
+int csp3_set_device(int device);
+
+/* ---- SpMV / SpMM ----------------------------------------------------------------------------------- */
+/* y = A*x.  Replaces csc_mat_vec_ff(m,n,Ap,Ai,Ax,x)->y, src/CSparse3/csc_numba.py:309-328. */
+int csp3_csc_mat_vec_ff_host(int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                             const double *x, double *y);
+/* Y += A*X.  Replaces sptools.csc_matvec, call site src/CSparse3/csc.py:374-379, source mirror
+ * src/sparsetools/csc.h:27-45. */
+int csp3_csc_matvec_host(int64_t n_row, int64_t n_col, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                         const double *Xx, double *Yx);
+/* Y[n_row,n_vecs] += A*X[n_col,n_vecs], row-major.  Replaces sptools.csc_matvecs, csc.py:409-415,
+ * src/sparsetools/csc.h:68-84. */
+int csp3_csc_matvecs_host(int64_t n_row, int64_t n_col, int64_t n_vecs, const int32_t *Ap, const int32_t *Ai,
+                          const double *Ax, const double *Xx, double *Yx);
+
+/* Device SpMV plan: CSC -> row-split CSR view built once per pattern (counting sort on device, as
+ * csc_to_csr csc_numba.py:360-397), then y = beta*y + A*x for `batch` value sets sharing the pattern.
+ *   Ax[batch, nnz] (stride_ax doubles between systems; 0 = one shared value set), x[batch, n], y[batch, m]. */
+typedef struct csp3_spmv_plan csp3_spmv_plan;
+int csp3_spmv_plan_create(int64_t m, int64_t n, const int32_t *Ap_dev, const int32_t *Ai_dev, void *stream,
+                          csp3_spmv_plan **plan);
+int csp3_spmv_plan_destroy(csp3_spmv_plan *plan);
+int csp3_spmv_batched(const csp3_spmv_plan *plan, int64_t batch, const double *Ax, int64_t stride_ax,
+                      const double *x, double *y, double beta, void *stream);
+
+/* ---- format conversion ------------------------------------------------------------------------------ */
+/* Replaces csc_transpose(m,n,Ap,Ai,Ax)->(n,m,Cp,Ci,Cx), csc_numba.py:400-436.  Cp[m+1], Ci/Cx[nnz]. */
+int csp3_csc_transpose_host(int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                            int32_t *Cp, int32_t *Ci, double *Cx);
+/* Replaces csc_to_csr(m,n,Ap,Ai,Ax,Bp,Bi,Bx), csc_numba.py:360-397 (Bp need not be pre-zeroed). */
+int csp3_csc_to_csr_host(int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                         int32_t *Bp, int32_t *Bi, double *Bx);
+/* Device form of both (the two are the same counting sort). */
+int csp3_csc_transpose(int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                       int32_t *Cp, int32_t *Ci, double *Cx, void *stream);
+
+/* ---- SpGEMM ------------------------------------------------------------------------------------------- */
+/* C = A*B, CSC, hash accumulation, two phases mirroring scipy's pass1/pass2 contract.
+ * symbolic: fills Cp[Bn+1], returns nnz(C) in *nnz (structural: explicit zeros kept, like csc_multiply_ff).
+ * numeric: fills Ci (row indices SORTED inside each column) and Cx.
+ * Replaces csc_multiply_ff, csc_numba.py:222-306 (caller CscMat.dot csc.py:483-500) and
+ * sptools.csc_matmat_pass1/pass2, csc.py:356-370, src/sparsetools/csc.h:115-137. */
+int csp3_spgemm_symbolic_host(int64_t Am, int64_t An, const int32_t *Ap, const int32_t *Ai, int64_t Bm,
+                              int64_t Bn, const int32_t *Bp, const int32_t *Bi, int32_t *Cp, int64_t *nnz);
+int csp3_spgemm_numeric_host(int64_t Am, int64_t An, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                             int64_t Bm, int64_t Bn, const int32_t *Bp, const int32_t *Bi, const double *Bx,
+                             const int32_t *Cp, int32_t *Ci, double *Cx);
+int csp3_spgemm_symbolic(int64_t Am, int64_t An, const int32_t *Ap, const int32_t *Ai, int64_t Bm, int64_t Bn,
+                         const int32_t *Bp, const int32_t *Bi, int32_t *Cp, int64_t *nnz_host, void *stream);
+int csp3_spgemm_numeric(int64_t Am, int64_t An, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                        int64_t Bm, int64_t Bn, const int32_t *Bp, const int32_t *Bi, const double *Bx,
+                        const int32_t *Cp, int32_t *Ci, double *Cx, void *stream);
+
+/* ---- host symbolic phase (runs once per pattern, cached by the caller) ---------------------------------- */
+/* q = amd(order, A): CSparse cs_amd.  order 0 natural, 1 A+A', 2 S'S (dense rows dropped), 3 A'A.  q[n]. */
+int csp3_csc_amd(int64_t order, int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, int32_t *q);
+/* parent = etree(A) (ata=0, upper part) or etree(A'A) (ata=1): CSparse cs_etree.  post = cs_post(parent). */
+int csp3_csc_etree(int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, int ata, int32_t *parent);
+int csp3_csc_post(int64_t n, const int32_t *parent, int32_t *post);
+
+/* Opaque symbolic object: ordering q, first factorisation with threshold partial pivoting (pinv and the
+ * L/U patterns it fixes, CSparse cs_lu layout: L unit diagonal first, U diagonal last, reach order inside
+ * columns), level sets and the device schedule derived from them.  Host arrays only until
+ * csp3_lu_upload(); plain data, safe to destroy at any time after the last kernel using it completed. */
+typedef struct csp3_lu_symbolic csp3_lu_symbolic;
+
+/* Analyse + first factorisation on the host.  All pointers are HOST pointers.  q_in may be NULL (then
+ * q = amd(order)).  Returns 0, or k+1 (>0) if no non-zero pivot exists in step k. */
+int csp3_lu_analyze(int64_t order, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                    const int32_t *q_in, double tol, csp3_lu_symbolic **sym);
+/* Same object from a KNOWN ordering, pivot sequence and L/U patterns (e.g. returned earlier by
+ * csp3_lu_get_pattern and cached by the caller): no factorisation is performed, values are not needed. */
+int csp3_lu_analyze_fixed(int64_t n, const int32_t *Ap, const int32_t *Ai, const int32_t *q, const int32_t *pinv,
+                          const int32_t *Lp, const int32_t *Li, const int32_t *Up, const int32_t *Ui,
+                          csp3_lu_symbolic **sym);
+int csp3_lu_destroy(csp3_lu_symbolic *sym);
+
+/* sizes: out[0]=n out[1]=nnzA out[2]=lnz out[3]=unz out[4]=refactor levels out[5]=L-solve levels
+ * out[6]=U-solve levels out[7]=refactor flops out[8]=bytes of device schedule */
+int csp3_lu_sizes(const csp3_lu_symbolic *sym, int64_t out[16]);
+/* Copy the integer results to caller HOST arrays (any may be NULL): q[n], pinv[n], Lp[n+1], Li[lnz],
+ * Up[n+1], Ui[unz]; and the first factorisation's values Lx[lnz], Ux[unz]. */
+int csp3_lu_get_pattern(const csp3_lu_symbolic *sym, int32_t *q, int32_t *pinv, int32_t *Lp, int32_t *Li,
+                        int32_t *Up, int32_t *Ui, double *Lx, double *Ux);
+/* Level sets.  kind 0 refactor (from U), 1 L-solve, 2 U-solve.  level[n], order[n], lptr[nlev+1]. */
+int csp3_lu_get_levels(const csp3_lu_symbolic *sym, int kind, int32_t *level, int32_t *order, int32_t *lptr);
+
+/* Replicate the schedule onto the current device (idempotent per device). */
+int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream);
+
+/* ---- device numeric phase: batched refactor / solve on one pattern --------------------------------------- */
+/* Refactor `batch` systems: Ax[batch, nnzA] (original CSC entry order) -> Lx[batch, lnz], Ux[batch, unz]
+ * in the cs_lu layout of csp3_lu_get_pattern().  status[batch] (device int32): 0 ok, k+1 = zero or
+ * non-finite pivot in column k (that system's factors are unusable; other systems are unaffected). */
+int csp3_lu_refactor_batched(const csp3_lu_symbolic *sym, int64_t batch, const double *Ax, double *Lx,
+                             double *Ux, int32_t *status, void *stream);
+/* Solve with existing factors: x = Q (U \ (L \ (P b))).  b[batch, n], x[batch, n] (may alias). */
+int csp3_lu_solve_batched(const csp3_lu_symbolic *sym, int64_t batch, const double *Lx, const double *Ux,
+                          const double *b, double *x, void *stream);
+/* Fused refactor + solve (factors written once to Lx/Ux if non-NULL, otherwise to `work`).
+ * work: csp3_lu_workspace_bytes(sym, batch) bytes of device scratch. */
+int64_t csp3_lu_workspace_bytes(const csp3_lu_symbolic *sym, int64_t batch);
+int csp3_lu_refactor_solve_batched(const csp3_lu_symbolic *sym, int64_t batch, const double *Ax,
+                                   const double *b, double *x, double *Lx, double *Ux, int32_t *status,
+                                   void *work, void *stream);
+
+/* Host-buffer batched refactor+solve: chunks the batch, overlapping H2D copies, kernels and D2H copies on
+ * internal streams.  Ax[batch, nnzA], b[batch, n], x[batch, n], status[batch] are HOST pointers (pinned
+ * memory gives full PCIe rate).  This is the end-to-end call the e2e benchmark times. */
+int csp3_lu_refactor_solve_host(csp3_lu_symbolic *sym, int64_t batch, const double *Ax, const double *b,
+                                double *x, int32_t *status);
+
+/* Host-buffer refactor / solve (synchronous; copy in, run the kernels, copy out). */
+int csp3_lu_refactor_host(csp3_lu_symbolic *sym, int64_t batch, const double *Ax, double *Lx, double *Ux,
+                          int32_t *status);
+int csp3_lu_solve_host(csp3_lu_symbolic *sym, int64_t batch, const double *Lx, const double *Ux,
+                       const double *b, double *x);
+
+/* One-shot: CSparse cs_lusol(order, A, b, tol) on the device path (analyse on host, refactor+solve on GPU).
+ * b is overwritten with x.  Host pointers. */
+int csp3_csc_lusol_host(int64_t order, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                        double *b, double tol);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSPARSE3_B200_H */
