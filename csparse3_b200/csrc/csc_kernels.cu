@@ -111,12 +111,14 @@ __global__ void k_spmv(int m, int n, i64 nnz_stride, const i32 *__restrict__ rp,
     const int sub = threadIdx.x % G;
     for (int r = (blockIdx.x * blockDim.x + threadIdx.x) / G; r < m; r += gridDim.x * blockDim.x / G) {
         const int beg = __ldg(rp + r), end = __ldg(rp + r + 1);
-        double s = 0.0;
+        // G == 1: sequential unfused sum in ascending column order starting from y -- bit-identical to the
+        // reference's column-scatter loop (csc_numba.py:325-327, sparsetools csc.h:36-44)
+        double s = (G == 1 && beta != 0.0) ? beta * yb[r] : 0.0;
         for (int t = beg + sub; t < end; t += G)
-            s += __ldg(Axb + __ldg(perm + t)) * __ldg(xb + __ldg(rc + t));
+            s = __dadd_rn(s, __dmul_rn(__ldg(Axb + __ldg(perm + t)), __ldg(xb + __ldg(rc + t))));
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (sub == 0) yb[r] = (beta == 0.0) ? s : beta * yb[r] + s;
+        if (sub == 0) yb[r] = (G == 1 || beta == 0.0) ? s : beta * yb[r] + s;
     }
 }
 
@@ -130,7 +132,8 @@ __global__ void k_spmm(int m, int nv, const i32 *__restrict__ rp, const i32 *__r
         const int r = (int)(idx / nv), v = (int)(idx - (i64)r * nv);
         const int beg = __ldg(rp + r), end = __ldg(rp + r + 1);
         double s = Y[idx];
-        for (int t = beg; t < end; ++t) s += __ldg(Ax + __ldg(perm + t)) * __ldg(X + (i64)__ldg(rc + t) * nv + v);
+        for (int t = beg; t < end; ++t)
+            s = __dadd_rn(s, __dmul_rn(__ldg(Ax + __ldg(perm + t)), __ldg(X + (i64)__ldg(rc + t) * nv + v)));
         Y[idx] = s;
     }
 }
@@ -281,14 +284,21 @@ int spmv_device(const SpmvPlanData &P, i64 batch, const double *Ax, i64 stride_a
                 double beta, cudaStream_t st)
 {
     if (batch <= 0 || P.m == 0) return 0;
-    const i64 rows_per_block = kThreads / 4;
+    // short rows (the power-grid / Laplacian case): one lane per row, exact reference summation order;
+    // long rows: 8 lanes per row with a shuffle reduction (order differs, results agree to rounding)
+    const bool wide = P.nnz > 48 * P.m;
+    const i64 rows_per_block = wide ? kThreads / 8 : kThreads;
     i64 gx = (P.m + rows_per_block - 1) / rows_per_block;
     gx = std::max<i64>(1, std::min<i64>(gx, 65535 * 16));
     for (i64 b0 = 0; b0 < batch; b0 += 65535) {
         const i64 nb = std::min<i64>(65535, batch - b0);
         dim3 grid((unsigned)gx, (unsigned)nb);
-        k_spmv<4><<<grid, kThreads, 0, st>>>((int)P.m, (int)P.n, stride_ax, P.rp, P.rc, P.perm, Ax + b0 * stride_ax,
-                                             x + b0 * P.n, y + b0 * P.m, beta);
+        if (wide)
+            k_spmv<8><<<grid, kThreads, 0, st>>>((int)P.m, (int)P.n, stride_ax, P.rp, P.rc, P.perm,
+                                                 Ax + b0 * stride_ax, x + b0 * P.n, y + b0 * P.m, beta);
+        else
+            k_spmv<1><<<grid, kThreads, 0, st>>>((int)P.m, (int)P.n, stride_ax, P.rp, P.rc, P.perm,
+                                                 Ax + b0 * stride_ax, x + b0 * P.n, y + b0 * P.m, beta);
     }
     CSP3_CUDA(cudaGetLastError());
     return 0;

@@ -96,10 +96,10 @@ __global__ void __launch_bounds__(1024) lu_refactor_kernel(const RefactorArgs a)
                     lv1 = Lxg[pd1.y + e];
                 }
                 const double mult = acc[pd0.x * S];
-                if (e < pd0.z) acc[off0 * S] -= lv0 * mult;
+                if (e < pd0.z) acc[off0 * S] = __dsub_rn(acc[off0 * S], __dmul_rn(lv0, mult));
                 for (int t = e + E; t < pd0.z; t += E) {
                     const int off = __ldg(a.upd_map + pd0.w + t);
-                    acc[off * S] -= Lxg[pd0.y + t] * mult;
+                    acc[off * S] = __dsub_rn(acc[off * S], __dmul_rn(Lxg[pd0.y + t], mult));
                 }
                 __syncwarp();
                 pd0 = pd1; pd1 = pd2; off0 = off1; lv0 = lv1;
@@ -163,12 +163,19 @@ __global__ void __launch_bounds__(1024) lu_solve_kernel(const SolveArgs a)
         for (int c = lbeg + warp * R + rsub; c < lend; c += nwarps * R) {
             const int r = __ldg(a.ls_order + c);
             const int pb = __ldg(a.lrow_ptr + r), pe = __ldg(a.lrow_ptr + r + 1);
-            double sum = 0.0;
-            for (int t = pb + e; t < pe; t += E)
-                sum += Lxg[__ldg(a.lrow_pos + t)] * y[(size_t)__ldg(a.lrow_col + t) * S + sys];
+            if (E == 1) {       // sequential, unfused: bit-identical to cs_lsolve's per-row update order
+                double s = y[(size_t)r * S + sys];
+                for (int t = pb; t < pe; ++t)
+                    s = __dsub_rn(s, __dmul_rn(Lxg[__ldg(a.lrow_pos + t)], y[(size_t)__ldg(a.lrow_col + t) * S + sys]));
+                y[(size_t)r * S + sys] = s;
+            } else {
+                double sum = 0.0;
+                for (int t = pb + e; t < pe; t += E)
+                    sum += Lxg[__ldg(a.lrow_pos + t)] * y[(size_t)__ldg(a.lrow_col + t) * S + sys];
 #pragma unroll
-            for (int o = E / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (e == 0) y[(size_t)r * S + sys] -= sum;
+                for (int o = E / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (e == 0) y[(size_t)r * S + sys] -= sum;
+            }
         }
         __syncthreads();
     }
@@ -178,14 +185,19 @@ __global__ void __launch_bounds__(1024) lu_solve_kernel(const SolveArgs a)
         for (int c = lbeg + warp * R + rsub; c < lend; c += nwarps * R) {
             const int r = __ldg(a.us_order + c);
             const int pb = __ldg(a.urow_ptr + r), pe = __ldg(a.urow_ptr + r + 1);
-            double sum = 0.0;
-            for (int t = pb + e; t < pe; t += E)
-                sum += Uxg[__ldg(a.urow_pos + t)] * y[(size_t)__ldg(a.urow_col + t) * S + sys];
+            const double d = Uxg[__ldg(a.Up + r + 1) - 1];
+            if (E == 1) {       // cs_usolve visits columns in DESCENDING order: row entries right to left
+                double s = y[(size_t)r * S + sys];
+                for (int t = pe - 1; t >= pb; --t)
+                    s = __dsub_rn(s, __dmul_rn(Uxg[__ldg(a.urow_pos + t)], y[(size_t)__ldg(a.urow_col + t) * S + sys]));
+                y[(size_t)r * S + sys] = s / d;
+            } else {
+                double sum = 0.0;
+                for (int t = pb + e; t < pe; t += E)
+                    sum += Uxg[__ldg(a.urow_pos + t)] * y[(size_t)__ldg(a.urow_col + t) * S + sys];
 #pragma unroll
-            for (int o = E / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (e == 0) {
-                const double d = Uxg[__ldg(a.Up + r + 1) - 1];
-                y[(size_t)r * S + sys] = (y[(size_t)r * S + sys] - sum) / d;
+                for (int o = E / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (e == 0) y[(size_t)r * S + sys] = (y[(size_t)r * S + sys] - sum) / d;
             }
         }
         __syncthreads();
@@ -281,10 +293,10 @@ int launch_solve(const DevSchedule &D, i64 batch, const double *Lx, const double
     }
     int rc;
     switch (S) {
-        case 1: rc = launch_solve_SE<1, 4>(a, warps, smem, st); break;
-        case 2: rc = launch_solve_SE<2, 4>(a, warps, smem, st); break;
-        case 4: rc = launch_solve_SE<4, 4>(a, warps, smem, st); break;
-        case 8: rc = launch_solve_SE<8, 4>(a, warps, smem, st); break;
+        case 1: rc = launch_solve_SE<1, 1>(a, warps, smem, st); break;
+        case 2: rc = launch_solve_SE<2, 1>(a, warps, smem, st); break;
+        case 4: rc = launch_solve_SE<4, 1>(a, warps, smem, st); break;
+        case 8: rc = launch_solve_SE<8, 1>(a, warps, smem, st); break;
         default: set_error("invalid solve bundle width %d", S); rc = -1;
     }
     if (scratch) CSP3_CUDA(cudaFreeAsync(scratch, st));

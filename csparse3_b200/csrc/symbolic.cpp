@@ -620,10 +620,10 @@ bool build_schedule(i64 n_, const i32 *Ap, const i32 *Ai, const std::vector<i32>
         }
         cd.a_cnt = a_cursor - cd.a_ptr;
         for (i32 t = cd.a_ptr; t < a_cursor; ++t) entry_of_slot[S.a_off[t]] = -1;
-        // update pairs in ascending pivot order (a valid topological order of the column's reach)
+        // update pairs in the STORED order of U(:,k): the topological (reach) order the first factorisation
+        // used, so every accumulator slot sees its updates in exactly the order of CSparse cs_lu / the oracle
         by_pivot.clear();
         for (i32 t = 0; t < cd.ucnt - 1; ++t) by_pivot.emplace_back(Ui[Up[k] + t], t);
-        std::sort(by_pivot.begin(), by_pivot.end());
         cd.pair_ptr = (i32)S.pairs.size();
         cd.pair_cnt = (i32)by_pivot.size();
         for (auto &jt : by_pivot) {

@@ -283,3 +283,15 @@ def lu_levels(n, Gp, Gi, kind):
 
 def lu_refactor_flops(n, Lp, Up, Ui):
     return int(lib().orc_lu_refactor_flops(i64(n), _pi(_i(Lp)), _pi(_i(Up)), _pi(_i(Ui))))
+
+
+def csc_lu_refactor_solve_batch(n, Ap, Ai, q, pinv, Lp, Li, Up, Ui, Ax, b, threads=1):
+    """Refactor + solve a batch on one pattern with `threads` OpenMP threads -> (x[batch, n], n_bad)."""
+    Ax = np.ascontiguousarray(Ax, dtype=np.float64).reshape(-1, int(Ap[n]))
+    b = np.ascontiguousarray(b, dtype=np.float64).reshape(-1, n)
+    x = np.empty_like(b)
+    qa = None if q is None else _i(q)
+    bad = lib().orc_csc_lu_refactor_solve_batch(i64(n), _pi(_i(Ap)), _pi(_i(Ai)), None if qa is None else _pi(qa),
+                                                _pi(_i(pinv)), _pi(_i(Lp)), _pi(_i(Li)), _pi(_i(Up)), _pi(_i(Ui)),
+                                                i64(Ax.shape[0]), _pi(Ax), _pi(b), _pi(x), C.c_int(int(threads)))
+    return x, int(bad)
