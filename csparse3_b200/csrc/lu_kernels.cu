@@ -45,6 +45,7 @@ template <int S>
 __global__ void __launch_bounds__(1024) lu_refactor_kernel(const RefactorArgs a)
 {
     constexpr int E = 32 / S;
+    constexpr int NC = (S >= 4) ? 4 : 2;      // register-prefetched chunks of E entries per pair
     extern __shared__ double smem[];
     __shared__ int fail[32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -68,41 +69,50 @@ __global__ void __launch_bounds__(1024) lu_refactor_kernel(const RefactorArgs a)
             const int up = c0.x, lp = c0.y, ucnt = c0.z, lcnt = c0.w;
             const int a_ptr = c1.x, a_cnt = c1.y, pair_ptr = c1.z, pair_cnt = c1.w;
             const int len = ucnt + lcnt - 1;
-            // prefetch the first two pair descriptors and the first L chunk while the accumulator is set up
+            // prefetch the first two pair descriptors and the first pair's L entries while the accumulator is set up
             int4 pd0 = make_int4(0, 0, 0, 0), pd1 = pd0;
             if (pair_cnt > 0) pd0 = ld_meta(a.pairs + pair_ptr);
             if (pair_cnt > 1) pd1 = ld_meta(a.pairs + pair_ptr + 1);
             for (int t = e; t < len; t += E) acc[t * S] = 0.0;
+            int off0[NC];
+            double lv0[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int t = e + c * E;
+                off0[c] = 0; lv0[c] = 0.0;
+                if (t < pd0.z) { off0[c] = __ldg(a.upd_map + pd0.w + t); lv0[c] = Lxg[pd0.y + t]; }
+            }
             __syncwarp();
             for (int t = e; t < a_cnt; t += E) {
                 const int src = __ldg(a.a_src + a_ptr + t);
                 const int off = __ldg(a.a_off + a_ptr + t);
                 acc[off * S] = __ldg(Axg + src);
             }
-            int off0 = 0;
-            double lv0 = 0.0;
-            if (e < pd0.z) {
-                off0 = __ldg(a.upd_map + pd0.w + e);
-                lv0 = Lxg[pd0.y + e];
-            }
             __syncwarp();
             for (int pi = 0; pi < pair_cnt; ++pi) {
                 int4 pd2 = make_int4(0, 0, 0, 0);
                 if (pi + 2 < pair_cnt) pd2 = ld_meta(a.pairs + pair_ptr + pi + 2);
-                int off1 = 0;
-                double lv1 = 0.0;
-                if (e < pd1.z) {                       // pd1 is all-zero past the end
-                    off1 = __ldg(a.upd_map + pd1.w + e);
-                    lv1 = Lxg[pd1.y + e];
+                // issue the loads of the NEXT pair (independent of the accumulator) before touching this one
+                int off1[NC];
+                double lv1[NC];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const int t = e + c * E;
+                    off1[c] = 0; lv1[c] = 0.0;
+                    if (t < pd1.z) { off1[c] = __ldg(a.upd_map + pd1.w + t); lv1[c] = Lxg[pd1.y + t]; }   // pd1 = 0 past the end
                 }
                 const double mult = acc[pd0.x * S];
-                if (e < pd0.z) acc[off0 * S] = __dsub_rn(acc[off0 * S], __dmul_rn(lv0, mult));
-                for (int t = e + E; t < pd0.z; t += E) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    if (e + c * E < pd0.z) acc[off0[c] * S] = __dsub_rn(acc[off0[c] * S], __dmul_rn(lv0[c], mult));
+                for (int t = e + NC * E; t < pd0.z; t += E) {
                     const int off = __ldg(a.upd_map + pd0.w + t);
                     acc[off * S] = __dsub_rn(acc[off * S], __dmul_rn(Lxg[pd0.y + t], mult));
                 }
                 __syncwarp();
-                pd0 = pd1; pd1 = pd2; off0 = off1; lv0 = lv1;
+                pd0 = pd1; pd1 = pd2;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) { off0[c] = off1[c]; lv0[c] = lv1[c]; }
             }
             // finalize: U(:,k) as accumulated, L(:,k) = x / pivot, unit diagonal first
             const double pivot = acc[(ucnt - 1) * S];
@@ -133,80 +143,75 @@ struct SolveArgs {
     double *scratch;       // global y[ceil(batch/S)][n*S] when shared memory is too small, else nullptr
 };
 
-// Lanes: S systems x R rows x E entry-lanes (S*R*E == 32).  y lives slot-major / system-minor.
-template <int S, int E>
+// One CTA per system.  y lives in shared memory (or in an HBM/L2 scratch row when n is too large).  A level's
+// rows are split over the warps; inside a warp, E lanes cooperate on one row (E = 4 in wide levels -> 8 rows
+// per warp, E = 32 in narrow levels).  The lanes first fetch the row's factor values and y operands in
+// PARALLEL and park the unfused products in shared memory; lane 0 of the group then subtracts them in the
+// reference's order (cs_lsolve: ascending column; cs_usolve: descending column), which keeps the result
+// bit-identical to the sequential algorithm while only one load round-trip is exposed per row.
+constexpr int kProdCap = 256;                 // products parked per warp
+
+template <bool UPPER>
+__device__ __forceinline__ void solve_phase(const SolveArgs &a, double *y, double *prod, const double *Fx,
+                                            const i32 *__restrict__ order, const i32 *__restrict__ lptr, int nlev,
+                                            const i32 *__restrict__ rp, const i32 *__restrict__ rc,
+                                            const i32 *__restrict__ rx)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int l = UPPER ? 0 : 1; l < nlev; ++l) {
+        const int lbeg = __ldg(lptr + l), lend = __ldg(lptr + l + 1);
+        const int E = (lend - lbeg > 2 * nwarps) ? 4 : 32;          // warp-uniform (CTA-uniform) per level
+        const int R = 32 / E, cap = kProdCap / R;
+        const int grp = lane / E, sub = lane - grp * E;
+        double *gp = prod + grp * cap;
+        for (int c0 = lbeg + warp * R; c0 < lend; c0 += nwarps * R) {
+            const int c = c0 + grp;
+            const bool active = c < lend;
+            int r = 0, pb = 0, pe = 0;
+            double s = 0.0, d = 1.0;
+            if (active) {
+                r = __ldg(order + c);
+                pb = __ldg(rp + r); pe = __ldg(rp + r + 1);
+                if (sub == 0) {
+                    s = y[r];
+                    if (UPPER) d = Fx[__ldg(a.Up + r + 1) - 1];
+                }
+            }
+            const int len = pe - pb;
+            for (int base = 0; __any_sync(0xffffffffu, base < len); base += cap) {
+                const int stop = min(len, base + cap);
+                for (int u = base + sub; u < stop; u += E) {
+                    const int t = UPPER ? (pe - 1 - u) : (pb + u);       // cs_usolve walks the row right to left
+                    gp[u - base] = __dmul_rn(Fx[__ldg(rx + t)], y[__ldg(rc + t)]);
+                }
+                __syncwarp();
+                if (sub == 0)
+                    for (int u = base; u < stop; ++u) s = __dsub_rn(s, gp[u - base]);
+                __syncwarp();
+            }
+            if (active && sub == 0) y[r] = UPPER ? s / d : s;
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(1024) lu_solve_kernel(const SolveArgs a)
 {
-    constexpr int R = 32 / (S * E);
     extern __shared__ double smem[];
-    double *y = a.scratch ? a.scratch + (size_t)blockIdx.x * a.n * S : smem;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int sys = lane / (R * E), rsub = (lane / E) % R, e = lane % E;
-    const i64 g0 = (i64)blockIdx.x * S;
-    const i64 g_raw = g0 + sys;
-    const bool valid = g_raw < a.batch;
-    const i64 g = valid ? g_raw : a.batch - 1;
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
+    const i64 g = blockIdx.x;
+    double *y = a.scratch ? a.scratch + (size_t)g * a.n : smem + (size_t)nwarps * kProdCap;
+    double *prod = smem + (size_t)warp * kProdCap;
     const double *Lxg = a.Lx + g * a.lnz;
     const double *Uxg = a.Ux + g * a.unz;
     const int n = a.n;
-
     // y = P b   (cs_ipvec: y[pinv[i]] = b[i])
-    for (int t = threadIdx.x; t < n * S; t += blockDim.x) {
-        const int s = t / n, i = t - s * n;
-        const i64 gs = (g0 + s < a.batch) ? g0 + s : a.batch - 1;
-        y[(size_t)__ldg(a.pinv + i) * S + s] = __ldg(a.b + gs * n + i);
-    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) y[__ldg(a.pinv + i)] = __ldg(a.b + g * n + i);
     __syncthreads();
-    // forward: y[r] -= sum_j L(r,j) y[j], rows level by level (level 0 rows have no entries)
-    for (int l = 1; l < a.ls_nlev; ++l) {
-        const int lbeg = __ldg(a.ls_lptr + l), lend = __ldg(a.ls_lptr + l + 1);
-        for (int c = lbeg + warp * R + rsub; c < lend; c += nwarps * R) {
-            const int r = __ldg(a.ls_order + c);
-            const int pb = __ldg(a.lrow_ptr + r), pe = __ldg(a.lrow_ptr + r + 1);
-            if (E == 1) {       // sequential, unfused: bit-identical to cs_lsolve's per-row update order
-                double s = y[(size_t)r * S + sys];
-                for (int t = pb; t < pe; ++t)
-                    s = __dsub_rn(s, __dmul_rn(Lxg[__ldg(a.lrow_pos + t)], y[(size_t)__ldg(a.lrow_col + t) * S + sys]));
-                y[(size_t)r * S + sys] = s;
-            } else {
-                double sum = 0.0;
-                for (int t = pb + e; t < pe; t += E)
-                    sum += Lxg[__ldg(a.lrow_pos + t)] * y[(size_t)__ldg(a.lrow_col + t) * S + sys];
-#pragma unroll
-                for (int o = E / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                if (e == 0) y[(size_t)r * S + sys] -= sum;
-            }
-        }
-        __syncthreads();
-    }
-    // backward: y[r] = (y[r] - sum_{j>r} U(r,j) y[j]) / U(r,r)
-    for (int l = 0; l < a.us_nlev; ++l) {
-        const int lbeg = __ldg(a.us_lptr + l), lend = __ldg(a.us_lptr + l + 1);
-        for (int c = lbeg + warp * R + rsub; c < lend; c += nwarps * R) {
-            const int r = __ldg(a.us_order + c);
-            const int pb = __ldg(a.urow_ptr + r), pe = __ldg(a.urow_ptr + r + 1);
-            const double d = Uxg[__ldg(a.Up + r + 1) - 1];
-            if (E == 1) {       // cs_usolve visits columns in DESCENDING order: row entries right to left
-                double s = y[(size_t)r * S + sys];
-                for (int t = pe - 1; t >= pb; --t)
-                    s = __dsub_rn(s, __dmul_rn(Uxg[__ldg(a.urow_pos + t)], y[(size_t)__ldg(a.urow_col + t) * S + sys]));
-                y[(size_t)r * S + sys] = s / d;
-            } else {
-                double sum = 0.0;
-                for (int t = pb + e; t < pe; t += E)
-                    sum += Uxg[__ldg(a.urow_pos + t)] * y[(size_t)__ldg(a.urow_col + t) * S + sys];
-#pragma unroll
-                for (int o = E / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                if (e == 0) y[(size_t)r * S + sys] = (y[(size_t)r * S + sys] - sum) / d;
-            }
-        }
-        __syncthreads();
-    }
+    solve_phase<false>(a, y, prod, Lxg, a.ls_order, a.ls_lptr, a.ls_nlev, a.lrow_ptr, a.lrow_col, a.lrow_pos);
+    solve_phase<true>(a, y, prod, Uxg, a.us_order, a.us_lptr, a.us_nlev, a.urow_ptr, a.urow_col, a.urow_pos);
     // x = Q y   (cs_ipvec: x[q[k]] = y[k])
-    for (int t = threadIdx.x; t < n * S; t += blockDim.x) {
-        const int s = t / n, k = t - s * n;
-        if (g0 + s < a.batch) a.x[(g0 + s) * n + __ldg(a.q + k)] = y[(size_t)k * S + s];
-    }
+    for (int k = threadIdx.x; k < n; k += blockDim.x) a.x[g * n + __ldg(a.q + k)] = y[k];
 }
 
 template <int S>
@@ -215,16 +220,6 @@ int launch_refactor_S(const RefactorArgs &a, int warps, size_t smem, cudaStream_
     CSP3_CUDA(cudaFuncSetAttribute(lu_refactor_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 grid = (a.batch + S - 1) / S;
     lu_refactor_kernel<S><<<(unsigned)grid, warps * 32, smem, st>>>(a);
-    CSP3_CUDA(cudaGetLastError());
-    return 0;
-}
-
-template <int S, int E>
-int launch_solve_SE(const SolveArgs &a, int warps, size_t smem, cudaStream_t st)
-{
-    CSP3_CUDA(cudaFuncSetAttribute(lu_solve_kernel<S, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const i64 grid = (a.batch + S - 1) / S;
-    lu_solve_kernel<S, E><<<(unsigned)grid, warps * 32, smem, st>>>(a);
     CSP3_CUDA(cudaGetLastError());
     return 0;
 }
@@ -245,7 +240,7 @@ int launch_refactor(const DevSchedule &D, i64 batch, const double *Ax, double *L
     // bundle width: enough systems per CTA to fill lanes, bounded by the batch and by shared memory
     int S = tuning().rf_S;
     if (S == 0) S = (batch >= 8 * kNumSMs) ? 4 : (batch >= 2 * kNumSMs ? 2 : 1);
-    int warps = tuning().rf_warps ? tuning().rf_warps : 8;
+    int warps = tuning().rf_warps ? tuning().rf_warps : 2;
     const int len = D.max_col_len > 0 ? D.max_col_len : 1;
     while (S > 1 && (size_t)len * S * 8 * 2 > kMaxSmem) S >>= 1;
     a.acc_stride = len * S + 2;                              // +2 doubles: stagger warps across banks
@@ -276,31 +271,23 @@ int launch_solve(const DevSchedule &D, i64 batch, const double *Lx, const double
     a.ls_nlev = D.ls_nlev; a.us_nlev = D.us_nlev;
     a.n = D.n; a.lnz = D.lnz; a.unz = D.unz;
     a.batch = batch; a.Lx = Lx; a.Ux = Ux; a.b = b; a.x = x; a.scratch = nullptr;
-    int S = tuning().sv_S;
-    if (S == 0) S = (batch >= 8 * kNumSMs) ? 2 : 1;
-    while (S > 1 && (size_t)D.n * S * 8 > kMaxSmem / 2) S >>= 1;
-    int warps = tuning().sv_warps ? tuning().sv_warps : 8;
-    size_t smem = (size_t)D.n * S * 8;
+    int warps = tuning().sv_warps ? tuning().sv_warps : 4;
+    size_t smem = (size_t)(D.n + warps * kProdCap) * 8;
     double *scratch = nullptr;
     if (smem > kMaxSmem) {                                   // y does not fit on chip: keep it in HBM/L2
-        const i64 grid = (batch + S - 1) / S;
-        CSP3_CUDA(cudaMallocAsync((void **)&scratch, (size_t)grid * D.n * S * 8, st));
+        CSP3_CUDA(cudaMallocAsync((void **)&scratch, (size_t)batch * D.n * 8, st));
         a.scratch = scratch;
-        smem = 0;
-        warps = 32;
-    } else if (smem > 64 * 1024 && !tuning().sv_warps) {
-        warps = 16;                                          // few CTAs per SM: more warps each
+        if (!tuning().sv_warps) warps = 16;
+        smem = (size_t)warps * kProdCap * 8;
+    } else if (smem > 96 * 1024 && !tuning().sv_warps) {
+        warps = 16;                                          // one or two CTAs per SM: more warps each
+        smem = (size_t)(D.n + warps * kProdCap) * 8;
     }
-    int rc;
-    switch (S) {
-        case 1: rc = launch_solve_SE<1, 1>(a, warps, smem, st); break;
-        case 2: rc = launch_solve_SE<2, 1>(a, warps, smem, st); break;
-        case 4: rc = launch_solve_SE<4, 1>(a, warps, smem, st); break;
-        case 8: rc = launch_solve_SE<8, 1>(a, warps, smem, st); break;
-        default: set_error("invalid solve bundle width %d", S); rc = -1;
-    }
+    CSP3_CUDA(cudaFuncSetAttribute(lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lu_solve_kernel<<<(unsigned)batch, warps * 32, smem, st>>>(a);
+    CSP3_CUDA(cudaGetLastError());
     if (scratch) CSP3_CUDA(cudaFreeAsync(scratch, st));
-    return rc;
+    return 0;
 }
 
 }  // namespace csp3

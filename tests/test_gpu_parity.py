@@ -73,10 +73,13 @@ def test_spmv_spmm_vs_oracle(seed):
     for m, n, dens in ((1, 1, 1.0), (17, 5, 0.3), (300, 411, 0.02), (64, 64, 0.9), (2000, 1500, 0.004)):
         Ap, Ai, Ax = _rand_csc(rng, m, n, dens)
         x = rng.standard_normal(n)
-        assert np.array_equal(B.csc_mat_vec_ff(m, n, Ap, Ai, Ax, x), orc.csc_mat_vec_ff(m, n, Ap, Ai, Ax, x))
+        # rows averaging > 48 entries take the 8-lanes-per-row kernel (shuffle reduction): same result to
+        # rounding; everything shorter follows the reference's summation order exactly
+        same = np.array_equal if Ap[n] <= 48 * m else (lambda u, v: np.allclose(u, v, rtol=1e-13, atol=1e-13))
+        assert same(B.csc_mat_vec_ff(m, n, Ap, Ai, Ax, x), orc.csc_mat_vec_ff(m, n, Ap, Ai, Ax, x))
         y0 = rng.standard_normal(m); y1 = y0.copy(); y2 = y0.copy()
         B.sptools.csc_matvec(m, n, Ap, Ai, Ax, x, y1); orc.csc_matvec(m, n, Ap, Ai, Ax, x, y2)
-        assert np.array_equal(y1, y2)
+        assert same(y1, y2)
         X = rng.standard_normal((n, 3)); Y1 = rng.standard_normal((m, 3)); Y2 = Y1.copy()
         B.sptools.csc_matvecs(m, n, 3, Ap, Ai, Ax, X, Y1); orc.csc_matvecs(m, n, 3, Ap, Ai, Ax, X, Y2)
         assert np.array_equal(Y1, Y2)
