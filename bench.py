@@ -201,16 +201,15 @@ def main():
     x_h = torch.empty((B, n), dtype=torch.float64, pin_memory=True)
     st_h = torch.empty(B, dtype=torch.int32, pin_memory=True)
     Ax_d, b_d = Ax_h.to(dev), b_h.to(dev)
-    Lx_d = torch.empty((B, sym.lnz), dtype=torch.float64, device=dev)
-    Ux_d = torch.empty((B, sym.unz), dtype=torch.float64, device=dev)
+    work_d = sym.workspace(B, dev)        # factors: written once by the refactor kernel, read once by the solve kernel
     x_d = torch.empty((B, n), dtype=torch.float64, device=dev)
     st_d = torch.empty(B, dtype=torch.int32, device=dev)
     log("[rank %d] setup %.1fs: n=%d nnzA=%d nnzLU=%d flops=%d levels=%d batch=%d" %
         (rank, time.perf_counter() - t_setup, n, sym.nnz, sym.nnz_lu, sym.flops, sym.nlev_refactor, B))
 
     def step():
-        sym.refactor(Ax_d, Lx_d, Ux_d, st_d)
-        sym.solve(Lx_d, Ux_d, b_d, x_d)
+        sym.refactor_ws(Ax_d, work_d, st_d)
+        sym.solve_ws(work_d, b_d, x_d)
 
     def barrier():
         if world > 1:
@@ -229,9 +228,9 @@ def main():
     barrier()
     for k in range(K):
         ev[k][0].record()
-        sym.refactor(Ax_d, Lx_d, Ux_d, st_d)
+        sym.refactor_ws(Ax_d, work_d, st_d)
         ev[k][1].record()
-        sym.solve(Lx_d, Ux_d, b_d, x_d)
+        sym.solve_ws(work_d, b_d, x_d)
         ev[k][2].record()
     barrier()
     clocks = sampler.stop()

@@ -53,6 +53,8 @@ SIGNATURES = {
     "csp3_lu_solve_batched": [vp, i64, vp, vp, vp, vp, vp],
     "csp3_lu_workspace_bytes": [vp, i64],
     "csp3_lu_refactor_solve_batched": [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp],
+    "csp3_lu_refactor_ws": [vp, i64, vp, vp, vp, vp],
+    "csp3_lu_solve_ws": [vp, i64, vp, vp, vp, vp],
     "csp3_lu_refactor_solve_host": [vp, i64, vp, vp, vp, vp],
     "csp3_lu_refactor_host": [vp, i64, vp, vp, vp, vp],
     "csp3_lu_solve_host": [vp, i64, vp, vp, vp, vp],

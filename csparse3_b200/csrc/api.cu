@@ -28,8 +28,8 @@ Tuning &tuning()
     static Tuning t = [] {
         Tuning v;
         auto env = [](const char *k) { const char *s = getenv(k); return s ? atoi(s) : 0; };
-        v.rf_S = env("CSP3_RF_S"); v.rf_warps = env("CSP3_RF_WARPS");
-        v.sv_S = env("CSP3_SV_S"); v.sv_warps = env("CSP3_SV_WARPS");
+        v.rf_S = env("CSP3_RF_S"); v.sv_S = env("CSP3_SV_S"); v.ws_S = env("CSP3_WS_S");
+        v.rf_win = env("CSP3_RF_WIN"); v.sv_stage = env("CSP3_SV_STAGE");
         return v;
     }();
     return t;
@@ -373,9 +373,7 @@ int csp3_lu_sizes(const csp3_lu_symbolic *sym, int64_t out[16])
     out[0] = sym->n; out[1] = sym->nnzA; out[2] = (i64)sym->F.Li.size(); out[3] = (i64)sym->F.Ui.size();
     out[4] = sym->S.lev_refactor.nlev(); out[5] = sym->S.lev_lsolve.nlev(); out[6] = sym->S.lev_usolve.nlev();
     out[7] = sym->S.flops;
-    out[8] = (i64)(sym->S.cols.size() * sizeof(ColDesc) + sym->S.pairs.size() * sizeof(PairDesc) +
-                   sym->S.upd_map.size() * 2 + sym->S.a_src.size() * 6 +
-                   (sym->S.lrow_col.size() + sym->S.urow_col.size()) * 8 + (size_t)sym->n * 4 * 12);
+    out[8] = (i64)(sym->S.rf_prog.bytes.size() + sym->S.ls_prog.bytes.size() + sym->S.us_prog.bytes.size());
     out[9] = sym->S.max_col_len;
     return 0;
 }
@@ -447,26 +445,9 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
     std::vector<Piece> pieces;
     size_t total = 0;
     auto add = [&](const void *src, size_t bytes) { total = (total + 255) & ~(size_t)255; pieces.push_back({src, bytes, total}); total += bytes; return pieces.size() - 1; };
-    const size_t i_cols = add(S.cols.data(), S.cols.size() * sizeof(ColDesc));
-    const size_t i_asrc = add(S.a_src.data(), S.a_src.size() * 4);
-    const size_t i_aoff = add(S.a_off.data(), S.a_off.size() * 2);
-    const size_t i_pairs = add(S.pairs.data(), S.pairs.size() * sizeof(PairDesc));
-    const size_t i_map = add(S.upd_map.data(), S.upd_map.size() * 2);
-    const size_t i_rfo = add(S.lev_refactor.order.data(), S.lev_refactor.order.size() * 4);
-    const size_t i_rfp = add(S.lev_refactor.lptr.data(), S.lev_refactor.lptr.size() * 4);
-    const size_t i_pinv = add(F.pinv.data(), F.pinv.size() * 4);
-    const size_t i_q = add(sym->q.data(), sym->q.size() * 4);
-    const size_t i_up = add(F.Up.data(), F.Up.size() * 4);
-    const size_t i_lrp = add(S.lrow_ptr.data(), S.lrow_ptr.size() * 4);
-    const size_t i_lrc = add(S.lrow_col.data(), S.lrow_col.size() * 4);
-    const size_t i_lrx = add(S.lrow_pos.data(), S.lrow_pos.size() * 4);
-    const size_t i_urp = add(S.urow_ptr.data(), S.urow_ptr.size() * 4);
-    const size_t i_urc = add(S.urow_col.data(), S.urow_col.size() * 4);
-    const size_t i_urx = add(S.urow_pos.data(), S.urow_pos.size() * 4);
-    const size_t i_lso = add(S.lev_lsolve.order.data(), S.lev_lsolve.order.size() * 4);
-    const size_t i_lsp = add(S.lev_lsolve.lptr.data(), S.lev_lsolve.lptr.size() * 4);
-    const size_t i_uso = add(S.lev_usolve.order.data(), S.lev_usolve.order.size() * 4);
-    const size_t i_usp = add(S.lev_usolve.lptr.data(), S.lev_usolve.lptr.size() * 4);
+    const size_t i_rf = add(S.rf_prog.bytes.data(), S.rf_prog.bytes.size());
+    const size_t i_ls = add(S.ls_prog.bytes.data(), S.ls_prog.bytes.size());
+    const size_t i_us = add(S.us_prog.bytes.data(), S.us_prog.bytes.size());
     total = (total + 255) & ~(size_t)255;
     char *arena = nullptr;
     if (cudaMalloc((void **)&arena, total ? total : 256) != cudaSuccess) { set_error("lu_upload: device allocation of %zu bytes failed", total); cudaGetLastError(); return CSP3_ERR_ALLOC; }
@@ -477,14 +458,10 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
     D.arena = arena; D.arena_bytes = total;
     D.n = (i32)sym->n; D.nnzA = (i32)sym->nnzA; D.lnz = (i32)F.Li.size(); D.unz = (i32)F.Ui.size();
     D.max_col_len = S.max_col_len;
-    D.cols = (const int4 *)at(i_cols); D.a_src = (const i32 *)at(i_asrc); D.a_off = (const uint16_t *)at(i_aoff);
-    D.pairs = (const int4 *)at(i_pairs); D.upd_map = (const uint16_t *)at(i_map);
-    D.rf_order = (const i32 *)at(i_rfo); D.rf_lptr = (const i32 *)at(i_rfp); D.rf_nlev = (i32)S.lev_refactor.nlev();
-    D.pinv = (const i32 *)at(i_pinv); D.q = (const i32 *)at(i_q); D.Up = (const i32 *)at(i_up);
-    D.lrow_ptr = (const i32 *)at(i_lrp); D.lrow_col = (const i32 *)at(i_lrc); D.lrow_pos = (const i32 *)at(i_lrx);
-    D.urow_ptr = (const i32 *)at(i_urp); D.urow_col = (const i32 *)at(i_urc); D.urow_pos = (const i32 *)at(i_urx);
-    D.ls_order = (const i32 *)at(i_lso); D.ls_lptr = (const i32 *)at(i_lsp); D.ls_nlev = (i32)S.lev_lsolve.nlev();
-    D.us_order = (const i32 *)at(i_uso); D.us_lptr = (const i32 *)at(i_usp); D.us_nlev = (i32)S.lev_usolve.nlev();
+    D.rf_prog = (const uint8_t *)at(i_rf); D.rf_prog_bytes = (i32)S.rf_prog.bytes.size(); D.rf_prog_stage = S.rf_prog.stage;
+    D.ls_prog = (const uint8_t *)at(i_ls); D.ls_prog_bytes = (i32)S.ls_prog.bytes.size(); D.ls_prog_stage = S.ls_prog.stage;
+    D.us_prog = (const uint8_t *)at(i_us); D.us_prog_bytes = (i32)S.us_prog.bytes.size(); D.us_prog_stage = S.us_prog.stage;
+    D.ls_nslots = S.ls.nslots; D.us_nslots = S.us.nslots;
     D.ready = true;
     return 0;
 }
@@ -507,7 +484,7 @@ int csp3_lu_refactor_batched(const csp3_lu_symbolic *sym, int64_t batch, const d
     const DevSchedule *D = current_schedule(sym);
     if (!D) return CSP3_ERR_ARG;
     if (batch < 0 || !Ax || !Lx || !Ux) { set_error("lu_refactor_batched: bad arguments"); return CSP3_ERR_ARG; }
-    return launch_refactor(*D, batch, Ax, Lx, Ux, status, (cudaStream_t)stream);
+    return launch_refactor(*D, batch, Ax, Lx, Ux, status, false, (cudaStream_t)stream);
 }
 
 int csp3_lu_solve_batched(const csp3_lu_symbolic *sym, int64_t batch, const double *Lx, const double *Ux,
@@ -515,14 +492,47 @@ int csp3_lu_solve_batched(const csp3_lu_symbolic *sym, int64_t batch, const doub
 {
     const DevSchedule *D = current_schedule(sym);
     if (!D) return CSP3_ERR_ARG;
-    if (batch < 0 || !Lx || !Ux || !b || !x) { set_error("lu_solve_batched: bad arguments"); return CSP3_ERR_ARG; }
-    return launch_solve(*D, batch, Lx, Ux, b, x, (cudaStream_t)stream);
+    if (batch < 0 || !Lx || !Ux || !b || !x || b == x) { set_error("lu_solve_batched: bad arguments (b and x must not alias)"); return CSP3_ERR_ARG; }
+    return launch_solve(*D, batch, Lx, Ux, b, x, nullptr, false, (cudaStream_t)stream);
 }
 
 int64_t csp3_lu_workspace_bytes(const csp3_lu_symbolic *sym, int64_t batch)
 {
     if (!sym || batch < 0) return -1;
-    return (int64_t)((sym->F.Li.size() + sym->F.Ui.size()) * 8) * batch + 512;
+    const i64 padded = (batch + 15) / 16 * 16;
+    return padded * (int64_t)(sym->F.Li.size() + sym->F.Ui.size() + (size_t)sym->n) * 8 + 512;
+}
+
+// workspace carve-up (bundle-interleaved): [ Lw | Uw | z ], each padded to whole bundles
+static void carve_workspace(const DevSchedule &D, i64 batch, void *work, double **Lw, double **Uw, double **z)
+{
+    const i64 padded = (batch + 15) / 16 * 16;
+    double *w = (double *)(((uintptr_t)work + 255) & ~(uintptr_t)255);
+    *Lw = w; w += padded * D.lnz;
+    *Uw = w; w += padded * D.unz;
+    *z = w;
+}
+
+int csp3_lu_refactor_ws(const csp3_lu_symbolic *sym, int64_t batch, const double *Ax, void *work,
+                        int32_t *status, void *stream)
+{
+    const DevSchedule *D = current_schedule(sym);
+    if (!D) return CSP3_ERR_ARG;
+    if (batch < 0 || !Ax || !work) { set_error("lu_refactor_ws: bad arguments"); return CSP3_ERR_ARG; }
+    double *Lw, *Uw, *z;
+    carve_workspace(*D, batch, work, &Lw, &Uw, &z);
+    return launch_refactor(*D, batch, Ax, Lw, Uw, status, true, (cudaStream_t)stream);
+}
+
+int csp3_lu_solve_ws(const csp3_lu_symbolic *sym, int64_t batch, void *work, const double *b, double *x,
+                     void *stream)
+{
+    const DevSchedule *D = current_schedule(sym);
+    if (!D) return CSP3_ERR_ARG;
+    if (batch < 0 || !work || !b || !x || b == x) { set_error("lu_solve_ws: bad arguments (b and x must not alias)"); return CSP3_ERR_ARG; }
+    double *Lw, *Uw, *z;
+    carve_workspace(*D, batch, work, &Lw, &Uw, &z);
+    return launch_solve(*D, batch, Lw, Uw, b, x, z, true, (cudaStream_t)stream);
 }
 
 int csp3_lu_refactor_solve_batched(const csp3_lu_symbolic *sym, int64_t batch, const double *Ax,
@@ -531,13 +541,14 @@ int csp3_lu_refactor_solve_batched(const csp3_lu_symbolic *sym, int64_t batch, c
 {
     const DevSchedule *D = current_schedule(sym);
     if (!D) return CSP3_ERR_ARG;
-    if (batch < 0 || !Ax || !b || !x) { set_error("lu_refactor_solve_batched: bad arguments"); return CSP3_ERR_ARG; }
-    if ((!Lx || !Ux) && !work) { set_error("lu_refactor_solve_batched: Lx/Ux or work must be given"); return CSP3_ERR_ARG; }
-    char *w = (char *)(((uintptr_t)work + 255) & ~(uintptr_t)255);
-    if (!Lx) { Lx = (double *)w; w += (size_t)D->lnz * 8 * batch; }
-    if (!Ux) { Ux = (double *)w; }
-    if (int rc = launch_refactor(*D, batch, Ax, Lx, Ux, status, (cudaStream_t)stream)) return rc;
-    return launch_solve(*D, batch, Lx, Ux, b, x, (cudaStream_t)stream);
+    if (batch < 0 || !Ax || !b || !x || b == x) { set_error("lu_refactor_solve_batched: bad arguments (b and x must not alias)"); return CSP3_ERR_ARG; }
+    if (Lx && Ux) {                                     // caller wants the factors: system-major API layout
+        if (int rc = launch_refactor(*D, batch, Ax, Lx, Ux, status, false, (cudaStream_t)stream)) return rc;
+        return launch_solve(*D, batch, Lx, Ux, b, x, nullptr, false, (cudaStream_t)stream);
+    }
+    if (!work) { set_error("lu_refactor_solve_batched: Lx and Ux, or work, must be given"); return CSP3_ERR_ARG; }
+    if (int rc = csp3_lu_refactor_ws(sym, batch, Ax, work, status, stream)) return rc;
+    return csp3_lu_solve_ws(sym, batch, work, b, x, stream);
 }
 
 int csp3_lu_refactor_solve_host(csp3_lu_symbolic *sym, int64_t batch, const double *Ax, const double *b,
@@ -561,20 +572,20 @@ int csp3_lu_refactor_solve_host(csp3_lu_symbolic *sym, int64_t batch, const doub
             CSP3_CUDA(cudaMalloc((void **)&G.Ax[s], (size_t)chunk * nnzA * 8 + 16));
             CSP3_CUDA(cudaMalloc((void **)&G.b[s], (size_t)chunk * n * 8 + 16));
             CSP3_CUDA(cudaMalloc((void **)&G.x[s], (size_t)chunk * n * 8 + 16));
-            CSP3_CUDA(cudaMalloc((void **)&G.Lx[s], (size_t)chunk * lnz * 8 + 16));
-            CSP3_CUDA(cudaMalloc((void **)&G.Ux[s], (size_t)chunk * unz * 8 + 16));
+            CSP3_CUDA(cudaMalloc((void **)&G.Lx[s], (size_t)csp3_lu_workspace_bytes(sym, chunk)));   // factor workspace
             CSP3_CUDA(cudaMalloc((void **)&G.status[s], (size_t)chunk * 4 + 16));
         }
         G.ready = true;
     }
+    (void)lnz; (void)unz;
     int slot = 0;
     for (i64 s0 = 0; s0 < batch; s0 += G.chunk, slot = (slot + 1) % 3) {
         const i64 cnt = std::min<i64>(G.chunk, batch - s0);
         cudaStream_t st = G.st[slot];
         CSP3_CUDA(cudaMemcpyAsync(G.Ax[slot], Ax + s0 * nnzA, (size_t)cnt * nnzA * 8, cudaMemcpyHostToDevice, st));
         CSP3_CUDA(cudaMemcpyAsync(G.b[slot], b + s0 * n, (size_t)cnt * n * 8, cudaMemcpyHostToDevice, st));
-        if (int rc = launch_refactor(D, cnt, G.Ax[slot], G.Lx[slot], G.Ux[slot], G.status[slot], st)) return rc;
-        if (int rc = launch_solve(D, cnt, G.Lx[slot], G.Ux[slot], G.b[slot], G.x[slot], st)) return rc;
+        if (int rc = csp3_lu_refactor_ws(sym, cnt, G.Ax[slot], G.Lx[slot], G.status[slot], st)) return rc;
+        if (int rc = csp3_lu_solve_ws(sym, cnt, G.Lx[slot], G.b[slot], G.x[slot], st)) return rc;
         CSP3_CUDA(cudaMemcpyAsync(x + s0 * n, G.x[slot], (size_t)cnt * n * 8, cudaMemcpyDeviceToHost, st));
         if (status) CSP3_CUDA(cudaMemcpyAsync(status + s0, G.status[slot], (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
     }

@@ -28,33 +28,27 @@ constexpr int kNumSMs = 148;   // B200
 struct DevSchedule {
     bool ready = false;
     i32 n = 0, nnzA = 0, lnz = 0, unz = 0, max_col_len = 0;
-    // refactor
-    const int4 *cols = nullptr;        // 2 x int4 per column (ColDesc)
-    const i32 *a_src = nullptr;
-    const uint16_t *a_off = nullptr;
-    const int4 *pairs = nullptr;       // PairDesc
-    const uint16_t *upd_map = nullptr;
-    const i32 *rf_order = nullptr, *rf_lptr = nullptr;
-    i32 rf_nlev = 0;
-    // solves
-    const i32 *pinv = nullptr, *q = nullptr, *Up = nullptr;
-    const i32 *lrow_ptr = nullptr, *lrow_col = nullptr, *lrow_pos = nullptr;
-    const i32 *urow_ptr = nullptr, *urow_col = nullptr, *urow_pos = nullptr;
-    const i32 *ls_order = nullptr, *ls_lptr = nullptr, *us_order = nullptr, *us_lptr = nullptr;
-    i32 ls_nlev = 0, us_nlev = 0;
+    // compiled programs (program.hpp), shared by every bundle
+    const uint8_t *rf_prog = nullptr, *ls_prog = nullptr, *us_prog = nullptr;
+    i32 rf_prog_bytes = 0, rf_prog_stage = 0, ls_prog_bytes = 0, ls_prog_stage = 0, us_prog_bytes = 0, us_prog_stage = 0;
+    i32 ls_nslots = 0, us_nslots = 0;
     void *arena = nullptr;             // single allocation backing all of the above
     size_t arena_bytes = 0;
 };
 
-// launchers (lu_kernels.cu)
+// launchers (lu_kernels.cu).  interleaved == false: Lx/Ux are system-major [batch][lnz|unz] (API layout);
+// interleaved == true: Lx/Ux/z point into a workspace in bundle-interleaved layout (see lu_kernels.cu).
 int launch_refactor(const DevSchedule &D, i64 batch, const double *Ax, double *Lx, double *Ux, i32 *status,
-                    cudaStream_t st);
+                    bool interleaved, cudaStream_t st);
 int launch_solve(const DevSchedule &D, i64 batch, const double *Lx, const double *Ux, const double *b,
-                 double *x, cudaStream_t st);
+                 double *x, double *z, bool interleaved, cudaStream_t st);
+int workspace_bundle_width(i64 batch);
 
-// tuning knobs (env CSP3_RF_S, CSP3_RF_WARPS, CSP3_SV_S, CSP3_SV_WARPS; 0 = automatic)
+// tuning knobs (env CSP3_RF_S, CSP3_SV_S: bundle width of the system-major kernels; CSP3_WS_S: bundle width of
+// the workspace path; CSP3_RF_WIN: entries of the recent-L ring; CSP3_SV_STAGE: entries per cp.async stage;
+// 0 = automatic)
 struct Tuning {
-    int rf_S = 0, rf_warps = 0, sv_S = 0, sv_warps = 0;
+    int rf_S = 0, sv_S = 0, ws_S = 0, rf_win = 0, sv_stage = 0;
 };
 Tuning &tuning();
 

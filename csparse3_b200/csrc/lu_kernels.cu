@@ -2,292 +2,419 @@
 //
 // No reference counterpart exists; semantics are the frozen-pattern / frozen-pivot
 // refactorisation and the cs_ipvec -> cs_lsolve -> cs_usolve -> cs_ipvec solve defined by
-// oracle/csp3_oracle.c (orc_csc_lu_refactor, orc_csc_lu_solve).
+// oracle/csp3_oracle.c (orc_csc_lu_refactor, orc_csc_lu_solve).  Both kernels reproduce the oracle's
+// floating-point operation order exactly (unfused multiply / subtract, IEEE division), so results are
+// bit-identical to the sequential algorithm and independent of bundle width, grid shape and GPU count.
 //
-// Layout in HBM (system-major, the reference's "leading batch dimension" convention):
-//   Ax[batch][nnzA]  values in the caller's CSC entry order
-//   Lx[batch][lnz], Ux[batch][unz]  factors in the cs_lu column layout of the symbolic object
-//   b[batch][n], x[batch][n]
-// All integer arrays (schedule) are shared by the whole batch and stay L2-resident.
+// Work decomposition: ONE WARP owns a bundle of S systems and executes the compiled program of the pattern
+// (program.hpp) for them, record after record, with no block- or grid-level barrier.  Lanes are split S x E
+// (E = 32/S lanes over the entries of a column), so all metadata is shared by S systems.  Power-grid factors
+// have elimination trees that are hundreds of levels deep and one or two columns wide, so parallelism inside a
+// system is scarce; throughput comes from thousands of independent bundles in flight.
 //
-// Refactor kernel: one CTA works on a bundle of S systems.  A warp owns one column of the current level
-// for all S systems at once: lanes are split S x E (E = 32/S lanes over the entries of a column), so index
-// loads are shared by S systems and every value load is a contiguous run per system.  The column is
-// accumulated in a per-warp shared-memory buffer (slot-major, system-minor -> no bank conflicts between
-// systems), updated left-looking with the finished columns L(:,j), j in U(:,k), then written ONCE to
-// Ux / Lx.  Levels are separated by __syncthreads(); L(:,j) values written in an earlier level are read
-// back through L1/L2 with plain (coherent) loads.
+// Data movement
+//   program  : global (L2-resident, shared by all bundles) -> shared-memory ring via cp.async, read with LDS
+//   A, b     : system-major input, pulled into L1 by prefetch directives compiled into the program
+//   L re-use : the last `win` L entries live in a shared-memory ring (the elimination order is a postorder,
+//              most re-reads are recent); older columns are prefetched into L1 two columns ahead
+//   factors  : written once, streamed back once by the sweeps
+//
+// Factor layouts in HBM
+//   system-major (API):      Lx[batch][lnz], Ux[batch][unz]                   (cs_lu column layout)
+//   bundle-interleaved (ws): Lw[bundle][lnz][S], Uw[bundle][unz][S], z[bundle][n][S]
+//     the workspace form of the fused refactor+solve path: one entry of all S systems of a bundle is one
+//     contiguous 8*S-byte run, so a warp-wide access to a column is one contiguous segment.
 #include "common.cuh"
+#include "program.hpp"
 
+#include <algorithm>
 #include <cmath>
 
 namespace csp3 {
 
 namespace {
 
+constexpr size_t kMaxSmem = 200 * 1024;
+constexpr int kProgStages = 4;      // ring slots of the program stream
+
+__device__ __forceinline__ void pf_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p)); }
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Sequential reader of a compiled program: stage s of the global byte stream lives in ring slot s % 4.
+// Invariant while a record starting in stage `cur` is read: stages <= cur + 1 have landed (records are shorter
+// than a stage, and the look-ahead never leaves stage cur + 1).
+struct ProgStream {
+    const uint8_t *src;
+    const uint8_t *ring;        // generic pointer to the shared-memory ring
+    unsigned ring_s;            // same, as a shared-window address
+    unsigned shift, mask, stage;
+    int nstages, cur;
+
+    __device__ __forceinline__ void issue(int s, int lane)
+    {
+        if (s < nstages) {
+            const unsigned dst = ring_s + ((unsigned)(s % kProgStages) << shift);
+            const uint8_t *from = src + ((size_t)s << shift);
+            for (unsigned u = lane * 16; u < stage; u += 32 * 16) cp_async16(dst + u, from + u);
+        }
+        cp_async_commit();                                   // exactly one group per stage, possibly empty
+    }
+    __device__ __forceinline__ void start(const uint8_t *program, int bytes, int stage_bytes, uint8_t *ring_ptr, int lane)
+    {
+        src = program; ring = ring_ptr; ring_s = (unsigned)__cvta_generic_to_shared(ring_ptr);
+        stage = (unsigned)stage_bytes; shift = 31 - __clz(stage_bytes); mask = kProgStages * stage - 1;
+        nstages = bytes >> shift; cur = 0;
+        issue(0, lane); issue(1, lane); issue(2, lane);
+        cp_async_wait<1>();
+        __syncwarp();
+    }
+    // call with the offset of the record about to be read
+    __device__ __forceinline__ void touch(unsigned p, int lane)
+    {
+        while ((int)(p >> shift) > cur) {
+            ++cur;
+            issue(cur + 2, lane);                            // overwrites stage cur-2: nothing reads it any more
+            cp_async_wait<1>();                              // stages <= cur + 1 have landed
+            __syncwarp();
+        }
+    }
+    template <class T>
+    __device__ __forceinline__ T ld(unsigned p) const { return *reinterpret_cast<const T *>(ring + (p & mask)); }
+};
+
 struct RefactorArgs {
-    const int4 *cols;
-    const i32 *a_src;
-    const uint16_t *a_off;
-    const int4 *pairs;
-    const uint16_t *upd_map;
-    const i32 *order, *lptr;
-    i32 nlev, n, nnzA, lnz, unz, acc_stride;
+    const uint8_t *prog;
+    i32 prog_bytes, prog_stage;
+    i32 n, nnzA, lnz, unz, acc_doubles, win_entries;
     i64 batch;
     const double *Ax;
     double *Lx, *Ux;
     i32 *status;
 };
 
-__device__ __forceinline__ int4 ld_meta(const int4 *p) { return __ldg(p); }
-
-template <int S>
-__global__ void __launch_bounds__(1024) lu_refactor_kernel(const RefactorArgs a)
+// ---------------------------------------------------------------------------------------------------------
+// refactorisation
+// ---------------------------------------------------------------------------------------------------------
+template <int S, bool IL>
+__global__ void __launch_bounds__(32) lu_refactor_kernel(const RefactorArgs a)
 {
     constexpr int E = 32 / S;
-    constexpr int NC = (S >= 4) ? 4 : 2;      // register-prefetched chunks of E entries per pair
+    constexpr int LS = IL ? S : 1;              // stride between consecutive entries of one system
     extern __shared__ double smem[];
     __shared__ int fail[32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int sys = lane / E, e = lane % E;
-    const i64 g_raw = (i64)blockIdx.x * S + sys;
+    const int lane = threadIdx.x, sys = lane / E, e = lane - sys * E;
+    const i64 b = blockIdx.x;
+    const i64 g_raw = b * S + sys;
     const bool valid = g_raw < a.batch;
     const i64 g = valid ? g_raw : a.batch - 1;
+    const bool store = IL || valid;             // padded lanes of the last bundle own workspace rows of their own
     const double *Axg = a.Ax + g * a.nnzA;
-    double *Lxg = a.Lx + g * a.lnz;
-    double *Uxg = a.Ux + g * a.unz;
-    double *acc = smem + (size_t)warp * a.acc_stride + sys;   // slot t of this system: acc[t * S]
+    double *Lg = IL ? a.Lx + (size_t)b * a.lnz * S + sys : a.Lx + g * a.lnz;
+    double *Ug = IL ? a.Ux + (size_t)b * a.unz * S + sys : a.Ux + g * a.unz;
+    double *acc = smem + sys;                   // accumulator slot t of this system: acc[t * S]
+    double *win = smem + a.acc_doubles + sys;   // ring of the most recent L entries: win[(p & wmask) * S]
+    const int wmask = a.win_entries - 1;
+    fail[lane] = INT32_MAX;
+    ProgStream ps;
+    ps.start(a.prog, a.prog_bytes, a.prog_stage, reinterpret_cast<uint8_t *>(smem + a.acc_doubles + (size_t)a.win_entries * S), lane);
 
-    if (threadIdx.x < 32) fail[threadIdx.x] = INT32_MAX;
-    __syncthreads();
+    unsigned p = 0;
+    for (int k = 0; k < a.n; ++k) {
+        ps.touch(p, lane);
+        const int2 ha = ps.ld<int2>(p), hb = ps.ld<int2>(p + 8);          // records are 8-byte aligned
+        const uint2 h2 = ps.ld<uint2>(p + 16);
+        const int up = ha.x, lp = ha.y;
+        const int ucnt = hb.x & 0xffff, lcnt = (int)((unsigned)hb.x >> 16);
+        const int a_cnt = hb.y & 0xffff, pair_cnt = (int)((unsigned)hb.y >> 16);
+        const int pf_cnt = (int)(h2.x & 0xffff), mpf_cnt = (int)(h2.x >> 16);
+        const unsigned pa = p + kRfHeader;                                   // A sources (i32)
+        const unsigned po = pa + 4 * a_cnt;                                  // A accumulator slots (u16)
+        const unsigned pp = (po + 2 * a_cnt + 7) & ~7u;                      // A prefetch directives (i32)
+        const unsigned pm = (pp + 4 * pf_cnt + 7) & ~7u;                     // far-source prefetch directives (8 B)
+        p = pm + 8 * mpf_cnt;                                                // first pair record
+        const int len = ucnt + lcnt - 1;
+        const int wlo = lp - a.win_entries;                                  // L entries >= wlo are in the ring
 
-    for (int l = 0; l < a.nlev; ++l) {
-        const int lbeg = __ldg(a.lptr + l), lend = __ldg(a.lptr + l + 1);
-        for (int c = lbeg + warp; c < lend; c += nwarps) {
-            const int k = __ldg(a.order + c);
-            const int4 c0 = ld_meta(a.cols + 2 * k), c1 = ld_meta(a.cols + 2 * k + 1);
-            const int up = c0.x, lp = c0.y, ucnt = c0.z, lcnt = c0.w;
-            const int a_ptr = c1.x, a_cnt = c1.y, pair_ptr = c1.z, pair_cnt = c1.w;
-            const int len = ucnt + lcnt - 1;
-            // prefetch the first two pair descriptors and the first pair's L entries while the accumulator is set up
-            int4 pd0 = make_int4(0, 0, 0, 0), pd1 = pd0;
-            if (pair_cnt > 0) pd0 = ld_meta(a.pairs + pair_ptr);
-            if (pair_cnt > 1) pd1 = ld_meta(a.pairs + pair_ptr + 1);
-            for (int t = e; t < len; t += E) acc[t * S] = 0.0;
-            int off0[NC];
-            double lv0[NC];
-#pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const int t = e + c * E;
-                off0[c] = 0; lv0[c] = 0.0;
-                if (t < pd0.z) { off0[c] = __ldg(a.upd_map + pd0.w + t); lv0[c] = Lxg[pd0.y + t]; }
+        // this column's A values (their lines were prefetched kPfCols columns ago)
+        int ao = -1;
+        double av = 0.0;
+        if (e < a_cnt) { ao = ps.ld<uint16_t>(po + 2 * e); av = __ldg(Axg + ps.ld<int>(pa + 4 * e)); }
+        // prefetch directives: A values of column k + kPfCols, far-back L columns of column k + kPfMissCols
+        for (int t = e; t < pf_cnt; t += E) pf_l1(Axg + ps.ld<int>(pp + 4 * t));
+        for (int m = 0; m < mpf_cnt; ++m) {
+            const uint2 d = ps.ld<uint2>(pm + 8 * m);
+            const int fl = (int)(d.y & 0xffff);
+            if (IL) {                                                        // one 128-byte line = 16/S bundle entries
+                constexpr int EPL = (16 / S > 0) ? 16 / S : 1;
+                if (lane * EPL < fl) pf_l1(Lg - sys + (size_t)((int)d.x + lane * EPL) * S);
+            } else if (e * 16 < fl) {
+                pf_l1(Lg + (int)d.x + e * 16);
             }
-            __syncwarp();
-            for (int t = e; t < a_cnt; t += E) {
-                const int src = __ldg(a.a_src + a_ptr + t);
-                const int off = __ldg(a.a_off + a_ptr + t);
-                acc[off * S] = __ldg(Axg + src);
-            }
-            __syncwarp();
-            for (int pi = 0; pi < pair_cnt; ++pi) {
-                int4 pd2 = make_int4(0, 0, 0, 0);
-                if (pi + 2 < pair_cnt) pd2 = ld_meta(a.pairs + pair_ptr + pi + 2);
-                // issue the loads of the NEXT pair (independent of the accumulator) before touching this one
-                int off1[NC];
-                double lv1[NC];
-#pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    const int t = e + c * E;
-                    off1[c] = 0; lv1[c] = 0.0;
-                    if (t < pd1.z) { off1[c] = __ldg(a.upd_map + pd1.w + t); lv1[c] = Lxg[pd1.y + t]; }   // pd1 = 0 past the end
+        }
+        for (int t = e; t < len; t += E) acc[t * S] = 0.0;
+        __syncwarp();
+        if (ao >= 0) acc[ao * S] = av;
+        for (int t = e + E; t < a_cnt; t += E) acc[ps.ld<uint16_t>(po + 2 * t) * S] = __ldg(Axg + ps.ld<int>(pa + 4 * t));
+        __syncwarp();
+
+        // left-looking updates, one pair record per off-diagonal entry of U(:,k), in the stored (topological) order
+        for (int pi = 0; pi < pair_cnt; ++pi) {
+            ps.touch(p, lane);
+            const int2 ph = ps.ld<int2>(p);
+            const int lstart = ph.x, moff = ph.y & 0xffff, llen = (int)((unsigned)ph.y >> 16);
+            const unsigned pmap = p + 8;
+            p = (pmap + 2 * llen + 7) & ~7u;
+            const double mult = acc[moff * S];
+            if (lstart >= wlo) {                                             // whole source column is in the ring
+                for (int t = e; t < llen; t += E) {
+                    const int off = ps.ld<uint16_t>(pmap + 2 * t);
+                    const double lv = win[((lstart + t) & wmask) * S];
+                    acc[off * S] = __dsub_rn(acc[off * S], __dmul_rn(lv, mult));
                 }
-                const double mult = acc[pd0.x * S];
-#pragma unroll
-                for (int c = 0; c < NC; ++c)
-                    if (e + c * E < pd0.z) acc[off0[c] * S] = __dsub_rn(acc[off0[c] * S], __dmul_rn(lv0[c], mult));
-                for (int t = e + NC * E; t < pd0.z; t += E) {
-                    const int off = __ldg(a.upd_map + pd0.w + t);
-                    acc[off * S] = __dsub_rn(acc[off * S], __dmul_rn(Lxg[pd0.y + t], mult));
+            } else {
+                for (int t = e; t < llen; t += E) {
+                    const int off = ps.ld<uint16_t>(pmap + 2 * t);
+                    const double lv = Lg[(size_t)(lstart + t) * LS];
+                    acc[off * S] = __dsub_rn(acc[off * S], __dmul_rn(lv, mult));
                 }
-                __syncwarp();
-                pd0 = pd1; pd1 = pd2;
-#pragma unroll
-                for (int c = 0; c < NC; ++c) { off0[c] = off1[c]; lv0[c] = lv1[c]; }
-            }
-            // finalize: U(:,k) as accumulated, L(:,k) = x / pivot, unit diagonal first
-            const double pivot = acc[(ucnt - 1) * S];
-            if (valid) {
-                for (int t = e; t < ucnt; t += E) Uxg[up + t] = acc[t * S];
-                if (e == 0) Lxg[lp] = 1.0;
-                for (int t = e; t < lcnt - 1; t += E) Lxg[lp + 1 + t] = acc[(ucnt + t) * S] / pivot;
-                if (e == 0 && !(fabs(pivot) > 0.0 && isfinite(pivot))) atomicMin(&fail[sys], k + 1);
             }
             __syncwarp();
         }
-        __syncthreads();
+
+        // finalize: U(:,k) as accumulated; L(:,k) = x / pivot, unit diagonal first; mirror L into the ring
+        const double pivot = acc[(ucnt - 1) * S];
+        if (store) {
+            for (int t = e; t < ucnt; t += E) Ug[(size_t)(up + t) * LS] = acc[t * S];
+            if (e == 0) Lg[(size_t)lp * LS] = 1.0;
+        }
+        for (int t = e; t < lcnt - 1; t += E) {
+            const double v = acc[(ucnt + t) * S] / pivot;
+            if (store) Lg[(size_t)(lp + 1 + t) * LS] = v;
+            win[((lp + 1 + t) & wmask) * S] = v;
+        }
+        if (e == 0 && valid && !(fabs(pivot) > 0.0 && isfinite(pivot))) atomicMin(&fail[sys], k + 1);
+        __syncwarp();
     }
-    if (a.status != nullptr && threadIdx.x < S) {
-        const i64 gs = (i64)blockIdx.x * S + threadIdx.x;
-        if (gs < a.batch) a.status[gs] = (fail[threadIdx.x] == INT32_MAX) ? 0 : fail[threadIdx.x];
+    cp_async_wait<0>();
+    if (a.status != nullptr && lane < S) {
+        const i64 gs = b * S + lane;
+        if (gs < a.batch) a.status[gs] = (fail[lane] == INT32_MAX) ? 0 : fail[lane];
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// triangular solves
+// ---------------------------------------------------------------------------------------------------------
 struct SolveArgs {
-    const i32 *pinv, *q, *Up;
-    const i32 *lrow_ptr, *lrow_col, *lrow_pos, *urow_ptr, *urow_col, *urow_pos;
-    const i32 *ls_order, *ls_lptr, *us_order, *us_lptr;
-    i32 ls_nlev, us_nlev, n, lnz, unz;
+    const uint8_t *lprog, *uprog;
+    i32 lprog_bytes, lprog_stage, uprog_bytes, uprog_stage;
+    i32 n, lnz, unz, nslots, ring_bytes;
     i64 batch;
     const double *Lx, *Ux, *b;
-    double *x;
-    double *scratch;       // global y[ceil(batch/S)][n*S] when shared memory is too small, else nullptr
+    double *x, *z;            // z: forward result, indexed like x; [bundle][n][S] (interleaved path only)
 };
 
-// One CTA per system.  y lives in shared memory (or in an HBM/L2 scratch row when n is too large).  A level's
-// rows are split over the warps; inside a warp, E lanes cooperate on one row (E = 4 in wide levels -> 8 rows
-// per warp, E = 32 in narrow levels).  The lanes first fetch the row's factor values and y operands in
-// PARALLEL and park the unfused products in shared memory; lane 0 of the group then subtracts them in the
-// reference's order (cs_lsolve: ascending column; cs_usolve: descending column), which keeps the result
-// bit-identical to the sequential algorithm while only one load round-trip is exposed per row.
-constexpr int kProdCap = 256;                 // products parked per warp
-
-template <bool UPPER>
-__device__ __forceinline__ void solve_phase(const SolveArgs &a, double *y, double *prod, const double *Fx,
-                                            const i32 *__restrict__ order, const i32 *__restrict__ lptr, int nlev,
-                                            const i32 *__restrict__ rp, const i32 *__restrict__ rc,
-                                            const i32 *__restrict__ rx)
+// One column-oriented sweep in exactly the order of cs_lsolve (columns ascending) / cs_usolve (descending).
+// The live rows of y sit in host-assigned shared-memory slots; factor values are read straight from global
+// memory behind a sequential L1 prefetcher (each column is one contiguous run).
+template <int S, bool IL, bool UPPER>
+__device__ __forceinline__ void sweep(const SolveArgs &a, ProgStream &ps, double *yc, const double *Fg,
+                                      const double *rhs_base, int rhs_stride, double *out_base, int out_stride,
+                                      bool out_ok, int lane, int sys, int e)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int l = UPPER ? 0 : 1; l < nlev; ++l) {
-        const int lbeg = __ldg(lptr + l), lend = __ldg(lptr + l + 1);
-        const int E = (lend - lbeg > 2 * nwarps) ? 4 : 32;          // warp-uniform (CTA-uniform) per level
-        const int R = 32 / E, cap = kProdCap / R;
-        const int grp = lane / E, sub = lane - grp * E;
-        double *gp = prod + grp * cap;
-        for (int c0 = lbeg + warp * R; c0 < lend; c0 += nwarps * R) {
-            const int c = c0 + grp;
-            const bool active = c < lend;
-            int r = 0, pb = 0, pe = 0;
-            double s = 0.0, d = 1.0;
-            if (active) {
-                r = __ldg(order + c);
-                pb = __ldg(rp + r); pe = __ldg(rp + r + 1);
-                if (sub == 0) {
-                    s = y[r];
-                    if (UPPER) d = Fx[__ldg(a.Up + r + 1) - 1];
-                }
-            }
-            const int len = pe - pb;
-            for (int base = 0; __any_sync(0xffffffffu, base < len); base += cap) {
-                const int stop = min(len, base + cap);
-                for (int u = base + sub; u < stop; u += E) {
-                    const int t = UPPER ? (pe - 1 - u) : (pb + u);       // cs_usolve walks the row right to left
-                    gp[u - base] = __dmul_rn(Fx[__ldg(rx + t)], y[__ldg(rc + t)]);
-                }
-                __syncwarp();
-                if (sub == 0)
-                    for (int u = base; u < stop; ++u) s = __dsub_rn(s, gp[u - base]);
-                __syncwarp();
-            }
-            if (active && sub == 0) y[r] = UPPER ? s / d : s;
-        }
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(1024) lu_solve_kernel(const SolveArgs a)
-{
-    extern __shared__ double smem[];
-    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
-    const i64 g = blockIdx.x;
-    double *y = a.scratch ? a.scratch + (size_t)g * a.n : smem + (size_t)nwarps * kProdCap;
-    double *prod = smem + (size_t)warp * kProdCap;
-    const double *Lxg = a.Lx + g * a.lnz;
-    const double *Uxg = a.Ux + g * a.unz;
+    constexpr int E = 32 / S;
+    constexpr int LS = IL ? S : 1;
+    constexpr int kAheadEntries = 96;                  // prefetch distance along the factor stream, in entries
     const int n = a.n;
-    // y = P b   (cs_ipvec: y[pinv[i]] = b[i])
-    for (int i = threadIdx.x; i < n; i += blockDim.x) y[__ldg(a.pinv + i)] = __ldg(a.b + g * n + i);
-    __syncthreads();
-    solve_phase<false>(a, y, prod, Lxg, a.ls_order, a.ls_lptr, a.ls_nlev, a.lrow_ptr, a.lrow_col, a.lrow_pos);
-    solve_phase<true>(a, y, prod, Uxg, a.us_order, a.us_lptr, a.us_nlev, a.urow_ptr, a.urow_col, a.urow_pos);
-    // x = Q y   (cs_ipvec: x[q[k]] = y[k])
-    for (int k = threadIdx.x; k < n; k += blockDim.x) a.x[g * n + __ldg(a.q + k)] = y[k];
+    unsigned p = 0;
+    for (int step = 0; step < n; ++step) {
+        ps.touch(p, lane);
+        const int2 ha = ps.ld<int2>(p), hb = ps.ld<int2>(p + 8);          // records are 8-byte aligned
+        const int outpos = ps.ld<int>(p + 16);
+        const int start = ha.x, rhs = ha.y;
+        const int slot = (int)(short)(hb.x & 0xffff), len = (int)((unsigned)hb.x >> 16);
+        const int nalloc = hb.y & 0xffff, pf_cnt = (int)((unsigned)hb.y >> 16);
+        const unsigned psl = p + kSvHeader;                                  // target slots (u16)
+        const unsigned pal = (psl + 2 * len + 7) & ~7u;                      // alloc rhs indices (i32)
+        const unsigned pas = pal + 4 * nalloc;                               // alloc slots (u16)
+        const unsigned ppf = (pas + 2 * nalloc + 7) & ~7u;                   // rhs prefetch directives (i32)
+        p = (ppf + 4 * pf_cnt + 7) & ~7u;
+
+        // operands that do not depend on y
+        int sl0 = 0;
+        double fv0 = 0.0;
+        if (e < len) { sl0 = ps.ld<uint16_t>(psl + 2 * e); fv0 = Fg[(size_t)(start + e) * LS]; }
+        int aslot = -1;
+        double arhs = 0.0;
+        if (e < nalloc) { aslot = ps.ld<uint16_t>(pas + 2 * e); arhs = rhs_base[(size_t)ps.ld<int>(pal + 4 * e) * rhs_stride]; }
+        double d = 1.0;
+        if (UPPER) d = Fg[(size_t)(start + len) * LS];
+        // prefetch: right-hand sides of the rows allocated kPfCols columns from now, next part of the factor stream
+        for (int t = e; t < pf_cnt; t += E) pf_l1(rhs_base + (size_t)ps.ld<int>(ppf + 4 * t) * rhs_stride);
+        {
+            const int ahead = UPPER ? start - kAheadEntries : start + len + kAheadEntries;
+            const int limit = UPPER ? a.unz : a.lnz;
+            if (ahead >= 0 && ahead < limit) {
+                if (IL) { if (lane == 0) pf_l1(Fg - sys + (size_t)ahead * S); }
+                else if (e == 0) pf_l1(Fg + ahead);
+            }
+        }
+        const double yraw = (slot >= 0) ? yc[slot * S] : rhs_base[(size_t)rhs * rhs_stride];
+        const double yj = UPPER ? yraw / d : yraw;
+        if (e == 0 && out_ok) out_base[(size_t)outpos * out_stride] = yj;
+        __syncwarp();                                               // y[j] is read before its slot is reused
+        if (aslot >= 0) yc[aslot * S] = arhs;
+        for (int t = e + E; t < nalloc; t += E)
+            yc[ps.ld<uint16_t>(pas + 2 * t) * S] = rhs_base[(size_t)ps.ld<int>(pal + 4 * t) * rhs_stride];
+        __syncwarp();
+        if (e < len) yc[sl0 * S] = __dsub_rn(yc[sl0 * S], __dmul_rn(fv0, yj));
+        for (int t = e + E; t < len; t += E) {
+            const int sl = ps.ld<uint16_t>(psl + 2 * t);
+            yc[sl * S] = __dsub_rn(yc[sl * S], __dmul_rn(Fg[(size_t)(start + t) * LS], yj));
+        }
+        __syncwarp();
+    }
+    cp_async_wait<0>();
+    __syncwarp();
 }
 
-template <int S>
-int launch_refactor_S(const RefactorArgs &a, int warps, size_t smem, cudaStream_t st)
+template <int S, bool IL>
+__global__ void __launch_bounds__(32) lu_solve_kernel(const SolveArgs a)
 {
-    CSP3_CUDA(cudaFuncSetAttribute(lu_refactor_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    constexpr int E = 32 / S;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x, sys = lane / E, e = lane - sys * E;
+    const i64 bnd = blockIdx.x;
+    const i64 g_raw = bnd * S + sys;
+    const bool valid = g_raw < a.batch;
+    const i64 g = valid ? g_raw : a.batch - 1;
+    const int n = a.n;
+    const double *Lg = IL ? a.Lx + (size_t)bnd * a.lnz * S + sys : a.Lx + g * a.lnz;
+    const double *Ug = IL ? a.Ux + (size_t)bnd * a.unz * S + sys : a.Ux + g * a.unz;
+    const double *bg = a.b + g * n;
+    double *xg = a.x + g * n;
+    // forward results are parked at their final x position: in the interleaved scratch z, or in x itself
+    double *park = IL ? a.z + (size_t)bnd * n * S + sys : xg;
+    const int park_stride = IL ? S : 1;
+    double *yc = smem + sys;                                        // live row in slot s: yc[s * S]
+    uint8_t *ring = reinterpret_cast<uint8_t *>(smem + (size_t)a.nslots * S);
+    ProgStream ps;
+    // y = L \ (P b)
+    ps.start(a.lprog, a.lprog_bytes, a.lprog_stage, ring, lane);
+    sweep<S, IL, false>(a, ps, yc, Lg, bg, 1, park, park_stride, IL || valid, lane, sys, e);
+    // x = Q (U \ y)
+    ps.start(a.uprog, a.uprog_bytes, a.uprog_stage, ring, lane);
+    sweep<S, IL, true>(a, ps, yc, Ug, park, park_stride, xg, 1, valid, lane, sys, e);
+}
+
+template <int S, bool IL>
+int launch_refactor_T(const RefactorArgs &a, size_t smem, cudaStream_t st)
+{
+    CSP3_CUDA(cudaFuncSetAttribute(lu_refactor_kernel<S, IL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 grid = (a.batch + S - 1) / S;
-    lu_refactor_kernel<S><<<(unsigned)grid, warps * 32, smem, st>>>(a);
+    lu_refactor_kernel<S, IL><<<(unsigned)grid, 32, smem, st>>>(a);
     CSP3_CUDA(cudaGetLastError());
     return 0;
 }
 
-constexpr size_t kMaxSmem = 200 * 1024;
+template <int S, bool IL>
+int launch_solve_T(const SolveArgs &a, size_t smem, cudaStream_t st)
+{
+    CSP3_CUDA(cudaFuncSetAttribute(lu_solve_kernel<S, IL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const i64 grid = (a.batch + S - 1) / S;
+    lu_solve_kernel<S, IL><<<(unsigned)grid, 32, smem, st>>>(a);
+    CSP3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int pow2_floor(int v) { int p = 1; while (2 * p <= v) p *= 2; return p; }
+
+int pick_width(int requested, i64 batch)
+{
+    if (requested == 1 || requested == 2 || requested == 4 || requested == 8 || requested == 16) return requested;
+    return (batch >= 8 * kNumSMs) ? 4 : (batch >= 2 * kNumSMs ? 2 : 1);
+}
 
 }  // namespace
 
+int workspace_bundle_width(i64 batch)
+{
+    const int S = tuning().ws_S;
+    if (S == 2 || S == 4 || S == 8 || S == 16) return S;
+    return (batch >= 16 * kNumSMs) ? 8 : 4;
+}
+
 int launch_refactor(const DevSchedule &D, i64 batch, const double *Ax, double *Lx, double *Ux, i32 *status,
-                    cudaStream_t st)
+                    bool interleaved, cudaStream_t st)
 {
     if (batch <= 0) return 0;
     RefactorArgs a;
-    a.cols = D.cols; a.a_src = D.a_src; a.a_off = D.a_off; a.pairs = D.pairs; a.upd_map = D.upd_map;
-    a.order = D.rf_order; a.lptr = D.rf_lptr; a.nlev = D.rf_nlev;
+    a.prog = D.rf_prog; a.prog_bytes = D.rf_prog_bytes; a.prog_stage = D.rf_prog_stage;
     a.n = D.n; a.nnzA = D.nnzA; a.lnz = D.lnz; a.unz = D.unz;
     a.batch = batch; a.Ax = Ax; a.Lx = Lx; a.Ux = Ux; a.status = status;
-    // bundle width: enough systems per CTA to fill lanes, bounded by the batch and by shared memory
-    int S = tuning().rf_S;
-    if (S == 0) S = (batch >= 8 * kNumSMs) ? 4 : (batch >= 2 * kNumSMs ? 2 : 1);
-    int warps = tuning().rf_warps ? tuning().rf_warps : 2;
+    int S = interleaved ? workspace_bundle_width(batch) : pick_width(tuning().rf_S, batch);
     const int len = D.max_col_len > 0 ? D.max_col_len : 1;
-    while (S > 1 && (size_t)len * S * 8 * 2 > kMaxSmem) S >>= 1;
-    a.acc_stride = len * S + 2;                              // +2 doubles: stagger warps across banks
-    while (warps > 1 && (size_t)a.acc_stride * warps * 8 > kMaxSmem) warps >>= 1;
-    const size_t smem = (size_t)a.acc_stride * warps * 8;
-    if (smem > kMaxSmem) { set_error("factor column too long for shared memory (%d entries)", len); return -1; }
-    switch (S) {
-        case 1: return launch_refactor_S<1>(a, warps, smem, st);
-        case 2: return launch_refactor_S<2>(a, warps, smem, st);
-        case 4: return launch_refactor_S<4>(a, warps, smem, st);
-        case 8: return launch_refactor_S<8>(a, warps, smem, st);
-        case 16: return launch_refactor_S<16>(a, warps, smem, st);
-        case 32: return launch_refactor_S<32>(a, warps, smem, st);
+    const size_t ring = (size_t)kProgStages * D.rf_prog_stage;
+    while (!interleaved && S > 1 && (size_t)len * S * 8 + ring > kMaxSmem / 2) S >>= 1;
+    a.acc_doubles = (len * S + 1) & ~1;                               // keep the program ring 16-byte aligned
+    const size_t acc_bytes = (size_t)a.acc_doubles * 8;
+    if (acc_bytes + ring + (size_t)64 * S * 8 > kMaxSmem) {
+        set_error("factor column too long for shared memory (%d entries, bundle width %d)", len, S);
+        return -1;
     }
+    int win = pow2_floor(std::max(64, tuning().rf_win > 0 ? tuning().rf_win : kCompileWindow));
+    while (win > 64 && acc_bytes + ring + (size_t)win * S * 8 > kMaxSmem) win >>= 1;
+    a.win_entries = win;
+    const size_t smem = acc_bytes + (size_t)win * S * 8 + ring;
+#define CSP3_RF(SV) return interleaved ? launch_refactor_T<SV, true>(a, smem, st) : launch_refactor_T<SV, false>(a, smem, st)
+    switch (S) {
+        case 1: return launch_refactor_T<1, false>(a, smem, st);
+        case 2: CSP3_RF(2);
+        case 4: CSP3_RF(4);
+        case 8: CSP3_RF(8);
+        case 16: CSP3_RF(16);
+    }
+#undef CSP3_RF
     set_error("invalid refactor bundle width %d", S);
     return -1;
 }
 
 int launch_solve(const DevSchedule &D, i64 batch, const double *Lx, const double *Ux, const double *b,
-                 double *x, cudaStream_t st)
+                 double *x, double *z, bool interleaved, cudaStream_t st)
 {
     if (batch <= 0) return 0;
     SolveArgs a;
-    a.pinv = D.pinv; a.q = D.q; a.Up = D.Up;
-    a.lrow_ptr = D.lrow_ptr; a.lrow_col = D.lrow_col; a.lrow_pos = D.lrow_pos;
-    a.urow_ptr = D.urow_ptr; a.urow_col = D.urow_col; a.urow_pos = D.urow_pos;
-    a.ls_order = D.ls_order; a.ls_lptr = D.ls_lptr; a.us_order = D.us_order; a.us_lptr = D.us_lptr;
-    a.ls_nlev = D.ls_nlev; a.us_nlev = D.us_nlev;
+    a.lprog = D.ls_prog; a.lprog_bytes = D.ls_prog_bytes; a.lprog_stage = D.ls_prog_stage;
+    a.uprog = D.us_prog; a.uprog_bytes = D.us_prog_bytes; a.uprog_stage = D.us_prog_stage;
     a.n = D.n; a.lnz = D.lnz; a.unz = D.unz;
-    a.batch = batch; a.Lx = Lx; a.Ux = Ux; a.b = b; a.x = x; a.scratch = nullptr;
-    int warps = tuning().sv_warps ? tuning().sv_warps : 4;
-    size_t smem = (size_t)(D.n + warps * kProdCap) * 8;
-    double *scratch = nullptr;
-    if (smem > kMaxSmem) {                                   // y does not fit on chip: keep it in HBM/L2
-        CSP3_CUDA(cudaMallocAsync((void **)&scratch, (size_t)batch * D.n * 8, st));
-        a.scratch = scratch;
-        if (!tuning().sv_warps) warps = 16;
-        smem = (size_t)warps * kProdCap * 8;
-    } else if (smem > 96 * 1024 && !tuning().sv_warps) {
-        warps = 16;                                          // one or two CTAs per SM: more warps each
-        smem = (size_t)(D.n + warps * kProdCap) * 8;
+    a.nslots = (std::max(D.ls_nslots, D.us_nslots) + 2) & ~1;          // keeps the ring 16-byte aligned for any S
+    a.batch = batch; a.Lx = Lx; a.Ux = Ux; a.b = b; a.x = x; a.z = z;
+    const size_t ring = (size_t)kProgStages * std::max(D.ls_prog_stage, D.us_prog_stage);
+    a.ring_bytes = (i32)ring;
+    int S = interleaved ? workspace_bundle_width(batch) : pick_width(tuning().sv_S, batch);
+    while (!interleaved && S > 1 && (size_t)a.nslots * S * 8 + ring > kMaxSmem / 2) S >>= 1;
+    const size_t smem = (size_t)a.nslots * S * 8 + ring;
+    if (smem > kMaxSmem) {
+        set_error("solve working set too large for shared memory (%d live rows, bundle width %d, %zu bytes)", a.nslots, S, smem);
+        return -1;
     }
-    CSP3_CUDA(cudaFuncSetAttribute(lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lu_solve_kernel<<<(unsigned)batch, warps * 32, smem, st>>>(a);
-    CSP3_CUDA(cudaGetLastError());
-    if (scratch) CSP3_CUDA(cudaFreeAsync(scratch, st));
-    return 0;
+#define CSP3_SV(SV) return interleaved ? launch_solve_T<SV, true>(a, smem, st) : launch_solve_T<SV, false>(a, smem, st)
+    switch (S) {
+        case 1: return launch_solve_T<1, false>(a, smem, st);
+        case 2: CSP3_SV(2);
+        case 4: CSP3_SV(4);
+        case 8: CSP3_SV(8);
+        case 16: CSP3_SV(16);
+    }
+#undef CSP3_SV
+    set_error("invalid solve bundle width %d", S);
+    return -1;
 }
 
 }  // namespace csp3

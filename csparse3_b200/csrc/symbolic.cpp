@@ -1,5 +1,6 @@
 // symbolic.cpp -- host symbolic phase (see symbolic.hpp).
 #include "symbolic.hpp"
+#include "program.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -579,6 +580,116 @@ LevelSet build_levels(i64 n, const std::vector<i32> &Gp, const std::vector<i32> 
 // ---------------------------------------------------------------------------------------------------------
 // device schedule
 // ---------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------
+// program compiler (formats in program.hpp)
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Emitter {
+    std::vector<uint8_t> &out;
+    size_t max_record = 0, rec_start = 0;
+    explicit Emitter(std::vector<uint8_t> &o) : out(o) {}
+    void i32v(i32 v) { const uint8_t *b = (const uint8_t *)&v; out.insert(out.end(), b, b + 4); }
+    void u16v(i32 v) { const uint16_t w = (uint16_t)v; const uint8_t *b = (const uint8_t *)&w; out.insert(out.end(), b, b + 2); }
+    void pad8() { while (out.size() & 7) out.push_back(0); }
+    void begin() { rec_start = out.size(); }
+    void end() { pad8(); max_record = std::max(max_record, out.size() - rec_start); }
+    void finish(Program &P)
+    {
+        i32 stage = 512;
+        while ((size_t)stage < max_record + 16) stage *= 2;
+        while (out.size() % (size_t)stage) out.push_back(0);
+        out.insert(out.end(), (size_t)stage, 0);            // one guard stage: look-ahead header reads stay in bounds
+        P.stage = stage;
+    }
+};
+
+void compile_programs(i64 n_, const std::vector<i32> &q, const Factor &F, Schedule &S)
+{
+    const i32 n = (i32)n_;
+    // ---- refactor: column header + A list + prefetch directives are ONE record, every pair is its own record
+    {
+        S.rf_prog = Program();
+        Emitter E(S.rf_prog.bytes);
+        for (i32 k = 0; k < n; ++k) {
+            const ColDesc &cd = S.cols[k];
+            const i32 kp = k + kPfCols;
+            const i32 pf_cnt = kp < n ? S.cols[kp].a_cnt : 0;
+            E.begin();
+            E.i32v(cd.up); E.i32v(cd.lp);
+            E.u16v(cd.ucnt); E.u16v(cd.lcnt); E.u16v(cd.a_cnt); E.u16v(cd.pair_cnt);
+            // far-back sources of column k + kPfMissCols (older than the recent-L ring)
+            std::vector<std::pair<i32, i32>> far;
+            const i32 km = k + kPfMissCols;
+            if (km < n) {
+                const ColDesc &cm = S.cols[km];
+                for (i32 pi = cm.pair_ptr; pi < cm.pair_ptr + cm.pair_cnt; ++pi)
+                    if (S.pairs[pi].lstart < cm.lp - kCompileWindow && S.pairs[pi].llen > 0)
+                        far.emplace_back(S.pairs[pi].lstart, S.pairs[pi].llen);
+            }
+            E.u16v(pf_cnt); E.u16v((i32)far.size()); E.i32v(0);
+            for (i32 t = 0; t < cd.a_cnt; ++t) E.i32v(S.a_src[cd.a_ptr + t]);
+            for (i32 t = 0; t < cd.a_cnt; ++t) E.u16v(S.a_off[cd.a_ptr + t]);
+            E.pad8();
+            for (i32 t = 0; t < pf_cnt; ++t) E.i32v(S.a_src[S.cols[kp].a_ptr + t]);
+            E.pad8();
+            for (auto &f : far) { E.i32v(f.first); E.u16v(f.second); E.u16v(0); }
+            E.end();
+            for (i32 pi = cd.pair_ptr; pi < cd.pair_ptr + cd.pair_cnt; ++pi) {
+                const PairDesc &pd = S.pairs[pi];
+                E.begin();
+                E.i32v(pd.lstart); E.u16v(pd.moff); E.u16v(pd.llen);
+                for (i32 t = 0; t < pd.llen; ++t) E.u16v(S.upd_map[(size_t)pd.mapstart + t]);
+                E.end();
+            }
+        }
+        E.finish(S.rf_prog);
+    }
+    // ---- sweeps
+    auto sweep = [&](const SolveStream &T, bool lower, Program &P) {
+        P = Program();
+        Emitter E(P.bytes);
+        // forward: right-hand sides come from b (original row prow[i]); results are parked at x-position q[j].
+        // backward: right-hand sides are those parked values (position q[i]); results go to q[j].
+        auto xpos = [&](i32 row) { return q.empty() ? row : q[row]; };
+        auto rhs_index = [&](i32 row) { return lower ? S.prow[row] : xpos(row); };
+        for (i32 step = 0; step < n; ++step) {
+            const i32 j = lower ? step : n - 1 - step;
+            const SolveCol &c = T.cols[j];
+            const i32 len = c.len_alloc & 0xffff, nalloc = (i32)((uint32_t)c.len_alloc >> 16);
+            const i32 stepp = step + kPfCols;
+            // right-hand sides needed kPfCols columns from now: that column's allocations and, when its own
+            // row was never touched, its own right-hand side
+            std::vector<i32> pf;
+            if (stepp < n) {
+                const i32 jp = lower ? stepp : n - 1 - stepp;
+                const SolveCol &cp = T.cols[jp];
+                const i32 na = (i32)((uint32_t)cp.len_alloc >> 16);
+                for (i32 t = 0; t < na; ++t) pf.push_back(rhs_index(T.alloc_row[cp.alloc_ptr + t]));
+                if (cp.slot < 0) pf.push_back(rhs_index(jp));
+            }
+            const i32 pf_cnt = (i32)pf.size();
+            E.begin();
+            E.i32v(c.start); E.i32v(rhs_index(j));
+            E.u16v(c.slot); E.u16v(len); E.u16v(nalloc); E.u16v(pf_cnt);
+            E.i32v(xpos(j)); E.i32v(0);
+            for (i32 t = 0; t < len; ++t) E.u16v(T.slot[(size_t)c.start + t]);
+            E.pad8();
+            for (i32 t = 0; t < nalloc; ++t) E.i32v(rhs_index(T.alloc_row[c.alloc_ptr + t]));
+            for (i32 t = 0; t < nalloc; ++t) E.u16v(T.alloc_slot[c.alloc_ptr + t]);
+            E.pad8();
+            for (i32 t = 0; t < pf_cnt; ++t) E.i32v(pf[t]);
+            E.end();
+        }
+        E.finish(P);
+    };
+    sweep(S.ls, true, S.ls_prog);
+    sweep(S.us, false, S.us_prog);
+    (void)F;
+}
+
+}  // namespace
+
 bool build_schedule(i64 n_, const i32 *Ap, const i32 *Ai, const std::vector<i32> &q, const Factor &F,
                     Schedule &S, const char **why)
 {
@@ -670,6 +781,47 @@ bool build_schedule(i64 n_, const i32 *Ap, const i32 *Ai, const std::vector<i32>
     };
     row_view(Lp, Li, true, S.lrow_ptr, S.lrow_col, S.lrow_pos);
     row_view(Up, Ui, false, S.urow_ptr, S.urow_col, S.urow_pos);
+    // streaming solves
+    S.prow.assign((size_t)n, 0);
+    for (i32 r = 0; r < n; ++r) S.prow[F.pinv[r]] = r;
+    auto stream = [n](const std::vector<i32> &Gp, const std::vector<i32> &Gi, bool lower, SolveStream &T,
+                      const char **why_) -> bool {
+        T = SolveStream();
+        T.cols.resize((size_t)n);
+        T.slot.assign(Gi.size(), 0);
+        std::vector<i32> slot_of((size_t)std::max(n, 1), -1), free_list;
+        i32 next_slot = 0;
+        for (i32 step = 0; step < n; ++step) {
+            const i32 j = lower ? step : n - 1 - step;
+            // strictly lower part of L(:,j) is [Lp[j]+1, Lp[j+1]); strictly upper part of U(:,j) is [Up[j], Up[j+1]-1)
+            const i32 beg = lower ? Gp[j] + 1 : Gp[j], end = lower ? Gp[j + 1] : Gp[j + 1] - 1;
+            SolveCol &c = T.cols[j];
+            c.slot = slot_of[j];
+            c.start = beg;
+            c.alloc_ptr = (i32)T.alloc_row.size();
+            if (slot_of[j] >= 0) { free_list.push_back(slot_of[j]); slot_of[j] = -1; }   // y[j] is read before any update below
+            i32 nalloc = 0;
+            for (i32 p = beg; p < end; ++p) {
+                const i32 i = Gi[p];
+                if (slot_of[i] < 0) {
+                    i32 sl;
+                    if (!free_list.empty()) { sl = free_list.back(); free_list.pop_back(); }
+                    else sl = next_slot++;
+                    slot_of[i] = sl;
+                    T.alloc_row.push_back(i);
+                    T.alloc_slot.push_back((uint16_t)sl);
+                    ++nalloc;
+                }
+                T.slot[p] = (uint16_t)slot_of[i];
+            }
+            if (end - beg > 65535 || next_slot > 65535) { *why_ = "solve wavefront exceeds 65535 rows"; return false; }
+            c.len_alloc = (end - beg) | (nalloc << 16);
+        }
+        T.nslots = next_slot;
+        return true;
+    };
+    if (!stream(Lp, Li, true, S.ls, why) || !stream(Up, Ui, false, S.us, why)) return false;
+    compile_programs(n, q, F, S);
     return true;
 }
 

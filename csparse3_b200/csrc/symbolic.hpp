@@ -58,6 +58,33 @@ struct PairDesc {           // 4 x int32, one per off-diagonal U entry, grouped 
     i32 mapstart;           // first entry of upd_map for this pair
 };
 
+// One triangular sweep in column order.  Column j owns the value range [start, start+len) of its factor array
+// (strictly lower part of L(:,j), or strictly upper part of U(:,j)); every entry updates the live row kept in
+// shared-memory slot `slot[p]`.  A row is given a slot the first time it is touched (alloc list of that
+// column: the slot is initialised with the row's right-hand side) and releases it when its own column is
+// reached.  slot_of_col[j] < 0: the row was never touched, its value is still the right-hand side.
+struct SolveCol {                  // 4 x int32
+    i32 slot;                      // slot holding y[j] when column j is reached, or -1
+    i32 start;                     // first value of the column's off-diagonal range
+    i32 len_alloc;                 // len | (number of allocs << 16)
+    i32 alloc_ptr;                 // first alloc of this column
+};
+struct SolveStream {
+    std::vector<SolveCol> cols;            // indexed by column
+    std::vector<uint16_t> slot;            // per factor entry (same indexing as Lx / Ux)
+    std::vector<i32> alloc_row;            // row (pivot numbering) whose right-hand side initialises the slot
+    std::vector<uint16_t> alloc_slot;
+    i32 nslots = 0;
+};
+
+// A compiled program: one byte stream of variable-length records, consumed strictly sequentially by every
+// warp through a shared-memory ring.  `stage` (a power of two) is >= the largest single record, `bytes` is a
+// multiple of `stage`.
+struct Program {
+    std::vector<uint8_t> bytes;
+    i32 stage = 0;
+};
+
 struct Schedule {
     // refactor
     std::vector<ColDesc> cols;
@@ -72,6 +99,11 @@ struct Schedule {
     std::vector<i32> urow_ptr, urow_col, urow_pos;
     LevelSet lev_lsolve, lev_usolve;
     i64 flops = 0;
+    // streaming (column-oriented) solves: cs_lsolve / cs_usolve order, live rows of y in host-assigned slots
+    SolveStream ls, us;
+    std::vector<i32> prow;             // prow[i] = original row r with pinv[r] == i  (y = P b: y[i] = b[prow[i]])
+    // compiled programs: what the kernels actually execute (see program.hpp for the record formats)
+    Program rf_prog, ls_prog, us_prog;
 };
 
 // Builds the schedule; returns false (with message) when a limit is exceeded (column longer than 65535

@@ -175,6 +175,32 @@ class LuSymbolic:
                 status.data_ptr(), None if work is None else work.data_ptr(), st), "csp3_lu_refactor_solve_batched")
         return x, status
 
+    def refactor_ws(self, Ax, work, status=None):
+        """Refactor into the internal bundle-interleaved factor workspace (fast path, see workspace())."""
+        import torch
+        Ax = self._dev(Ax, self.nnz, "Ax")
+        B = Ax.numel() // self.nnz
+        with torch.cuda.device(Ax.device):
+            st = torch.cuda.current_stream().cuda_stream
+            self._upload(Ax.device.index, st)
+            status = torch.empty(B, dtype=torch.int32, device=Ax.device) if status is None else status
+            check(_lib.lib().csp3_lu_refactor_ws(self._h, B, Ax.data_ptr(), work.data_ptr(), status.data_ptr(), st),
+                  "csp3_lu_refactor_ws")
+        return status
+
+    def solve_ws(self, work, b, x=None):
+        """Solve with the factors left in `work` by refactor_ws (same batch)."""
+        import torch
+        b = self._dev(b, self.n, "b")
+        B = b.numel() // self.n
+        with torch.cuda.device(b.device):
+            st = torch.cuda.current_stream().cuda_stream
+            self._upload(b.device.index, st)
+            x = torch.empty_like(b) if x is None else x
+            check(_lib.lib().csp3_lu_solve_ws(self._h, B, work.data_ptr(), b.data_ptr(), x.data_ptr(), st),
+                  "csp3_lu_solve_ws")
+        return x
+
     def workspace(self, batch, device):
         import torch
         return torch.empty(_lib.lib().csp3_lu_workspace_bytes(self._h, batch), dtype=torch.uint8, device=device)

@@ -136,15 +136,24 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream);
  * non-finite pivot in column k (that system's factors are unusable; other systems are unaffected). */
 int csp3_lu_refactor_batched(const csp3_lu_symbolic *sym, int64_t batch, const double *Ax, double *Lx,
                              double *Ux, int32_t *status, void *stream);
-/* Solve with existing factors: x = Q (U \ (L \ (P b))).  b[batch, n], x[batch, n] (may alias). */
+/* Solve with existing factors: x = Q (U \ (L \ (P b))).  b[batch, n], x[batch, n] (must not alias). */
 int csp3_lu_solve_batched(const csp3_lu_symbolic *sym, int64_t batch, const double *Lx, const double *Ux,
                           const double *b, double *x, void *stream);
-/* Fused refactor + solve (factors written once to Lx/Ux if non-NULL, otherwise to `work`).
- * work: csp3_lu_workspace_bytes(sym, batch) bytes of device scratch. */
+/* Fused refactor + solve.  With Lx and Ux non-NULL the factors are returned in the API layout; with both
+ * NULL they stay in `work` (csp3_lu_workspace_bytes(sym, batch) bytes of device scratch) in the internal
+ * bundle-interleaved layout, which is the fast path. */
 int64_t csp3_lu_workspace_bytes(const csp3_lu_symbolic *sym, int64_t batch);
 int csp3_lu_refactor_solve_batched(const csp3_lu_symbolic *sym, int64_t batch, const double *Ax,
                                    const double *b, double *x, double *Lx, double *Ux, int32_t *status,
                                    void *work, void *stream);
+
+/* The two halves of the fused path, with the factors kept in `work` in the library's internal
+ * bundle-interleaved layout (opaque to the caller; only csp3_lu_solve_ws with the same batch reads it).
+ * This is the fast path: each factor entry of a bundle of systems is one contiguous run in HBM. */
+int csp3_lu_refactor_ws(const csp3_lu_symbolic *sym, int64_t batch, const double *Ax, void *work,
+                        int32_t *status, void *stream);
+int csp3_lu_solve_ws(const csp3_lu_symbolic *sym, int64_t batch, void *work, const double *b, double *x,
+                     void *stream);
 
 /* Host-buffer batched refactor+solve: chunks the batch, overlapping H2D copies, kernels and D2H copies on
  * internal streams.  Ax[batch, nnzA], b[batch, n], x[batch, n], status[batch] are HOST pointers (pinned

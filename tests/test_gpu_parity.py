@@ -184,27 +184,35 @@ def test_lu_small_matrices_bit_exact(order, tol):
         assert np.array_equal(x, ox) and (status == 0).all()
 
 
-@pytest.mark.parametrize("S", [1, 2, 4, 8, 32])
-def test_lu_grid118_bundle_widths_agree(S, monkeypatch):
-    """Every bundle width must give the same bits (shard/bundle invariance); ragged batch sizes."""
-    import torch
+@pytest.mark.parametrize("path,S", [("sm", 1), ("sm", 2), ("sm", 4), ("sm", 8), ("sm", 16),
+                                    ("ws", 2), ("ws", 4), ("ws", 8), ("ws", 16)])
+def test_lu_grid118_bundle_widths_agree(path, S):
+    """Every bundle width and both factor layouts (system-major API / interleaved workspace) must give the
+    same bits (shard / bundle invariance); ragged batch size; tiny ring and stage sizes to exercise wrap-around."""
+    import os, subprocess, sys
     g = synth.GridCase(118)
     n, Ap, Ai, Ax0 = g.base_jacobian()
     sym = LuSymbolic(n, Ap, Ai, Ax0)
     Axb, bb = g.jacobian_batch(0, 37)
     oLx, oUx, ox = _oracle_batch(sym, n, Ap, Ai, Axb, bb)
-    import subprocess, sys, os, json
-    # the tuning knobs are read once per process: run the width under test in a child process
-    code = ("import sys, numpy as np; sys.path.insert(0, %r); from csparse3_b200 import synth; "
+    # the tuning knobs are read once per process: run the setting under test in a child process
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, numpy as np, torch; sys.path.insert(0, %r); from csparse3_b200 import synth; "
             "from csparse3_b200.lu import LuSymbolic; g = synth.GridCase(118); n, Ap, Ai, Ax0 = g.base_jacobian(); "
             "sym = LuSymbolic(n, Ap, Ai, Ax0); Axb, bb = g.jacobian_batch(0, 37); "
             "Lx, Ux, st = sym.refactor_host(Axb); x = sym.solve_host(Lx, Ux, bb); "
-            "np.savez(sys.argv[1], Lx=Lx, Ux=Ux, x=x, st=st)") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = os.path.join(os.environ.get("TMPDIR", "/tmp"), "csp3_w%d.npz" % S)
-    env = dict(os.environ, CSP3_RF_S=str(S), CSP3_SV_S=str(min(S, 8)))
+            "xw, stw = sym.refactor_solve(torch.as_tensor(Axb).cuda(), torch.as_tensor(bb).cuda()); "
+            "np.savez(sys.argv[1], Lx=Lx, Ux=Ux, x=x, st=st, xw=xw.cpu().numpy(), stw=stw.cpu().numpy())") % root
+    out = os.path.join(os.environ.get("TMPDIR", "/tmp"), "csp3_w%s%d.npz" % (path, S))
+    env = dict(os.environ, CSP3_RF_WIN="64", CSP3_SV_STAGE="64")
+    if path == "sm":
+        env.update(CSP3_RF_S=str(S), CSP3_SV_S=str(S))
+    else:
+        env.update(CSP3_WS_S=str(S))
     subprocess.check_call([sys.executable, "-c", code, out], env=env)
     r = np.load(out)
     assert np.array_equal(r["Lx"], oLx) and np.array_equal(r["Ux"], oUx) and np.array_equal(r["x"], ox) and (r["st"] == 0).all()
+    assert np.array_equal(r["xw"], ox) and (r["stw"] == 0).all()          # fused path through the workspace layout
 
 
 def test_lu_config3_sample_device_api():

@@ -35,13 +35,23 @@ def child(args):
     Ux = torch.empty((B, sym.unz), dtype=torch.float64, device="cuda")
     x = torch.empty((B, n), dtype=torch.float64, device="cuda")
     st = torch.empty(B, dtype=torch.int32, device="cuda")
+    work = sym.workspace(B, "cuda")
+    ws = os.environ.get("CSP3_PATH", "ws") == "ws"
+
+    def run_rf():
+        if ws: sym.refactor_ws(Ax, work, st)
+        else: sym.refactor(Ax, Lx, Ux, st)
+
+    def run_sv():
+        if ws: sym.solve_ws(work, b, x)
+        else: sym.solve(Lx, Ux, b, x)
     for _ in range(2):
-        sym.refactor(Ax, Lx, Ux, st); sym.solve(Lx, Ux, b, x)
+        run_rf(); run_sv()
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     rf, sv = [], []
     for _ in range(args.iters):
-        ev[0].record(); sym.refactor(Ax, Lx, Ux, st); ev[1].record(); sym.solve(Lx, Ux, b, x); ev[2].record()
+        ev[0].record(); run_rf(); ev[1].record(); run_sv(); ev[2].record()
         torch.cuda.synchronize()
         rf.append(ev[0].elapsed_time(ev[1])); sv.append(ev[1].elapsed_time(ev[2]))
     ok = int(st.abs().max().item()) == 0
@@ -50,8 +60,7 @@ def child(args):
     same = bool(np.array_equal(x[:xo.shape[0]].cpu().numpy(), xo))
     peak = 6535.1
     brf = (8 * sym.nnz + 8 * sym.nnz_lu) * B; bsv = (8 * sym.nnz_lu + 16 * n) * B
-    print(json.dumps({"rf_S": os.environ.get("CSP3_RF_S"), "rf_warps": os.environ.get("CSP3_RF_WARPS"),
-                      "sv_warps": os.environ.get("CSP3_SV_WARPS"), "batch": B,
+    print(json.dumps({"cfg": os.environ.get("CSP3_CFG"), "batch": B,
                       "rf_ms": min(rf), "sv_ms": min(sv), "rf_frac": brf / (min(rf) * 1e-3) / 1e9 / peak,
                       "sv_frac": bsv / (min(sv) * 1e-3) / 1e9 / peak,
                       "sys_per_s": B / ((min(rf) + min(sv)) * 1e-3), "status_ok": ok, "bit_exact": same}), flush=True)
@@ -62,8 +71,7 @@ def main():
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--iters", type=int, default=5)
-    ap.add_argument("--rf", default="4x2")
-    ap.add_argument("--sv", default="4")
+    ap.add_argument("--cfg", default="ws:S=8;ws:S=4;sm:RFS=4,SVS=4")
     ap.add_argument("--child", action="store_true")
     args = ap.parse_args()
     if args.child:
@@ -82,11 +90,14 @@ def main():
         Ax, b = gen(0, 256)
         x, bad = orc.csc_lu_refactor_solve_batch(n, Ap, Ai, sym.q, sym.pinv, sym.Lp, sym.Li, sym.Up, sym.Ui, Ax[:32], b[:32], 8)
         np.savez(cache, Ax=Ax, b=b, x=x)
-    rfs = [t.split("x") for t in args.rf.split(",")]
-    svs = args.sv.split(",")
-    combos = [(s, w, svs[0]) for s, w in rfs] + [(rfs[0][0], rfs[0][1], v) for v in svs[1:]]
-    for s, w, v in combos:
-        env = dict(os.environ, CSP3_RF_S=s, CSP3_RF_WARPS=w, CSP3_SV_WARPS=v)
+    # --cfg "ws:S=8,WIN=1024,STAGE=128;ws:S=4;sm:RFS=4,SVS=4"
+    for cfg in args.cfg.split(";"):
+        path, _, kv = cfg.partition(":")
+        env = dict(os.environ, CSP3_PATH=path, CSP3_CFG=cfg)
+        names = {"S": "CSP3_WS_S", "WIN": "CSP3_RF_WIN", "STAGE": "CSP3_SV_STAGE", "RFS": "CSP3_RF_S", "SVS": "CSP3_SV_S"}
+        for item in filter(None, kv.split(",")):
+            k, v = item.split("=")
+            env[names[k]] = v
         subprocess.call([sys.executable, os.path.abspath(__file__), "--child", "--workload", args.workload,
                          "--batch", str(args.batch), "--iters", str(args.iters)], env=env)
 
