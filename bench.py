@@ -305,7 +305,7 @@ def main():
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(B * (sym.nnz + n) * 8), "d2h_bytes_per_step": int(B * (n * 8 + 4)),
                     "ms_per_step": e2e_ms, "api": "csp3_lu_refactor_solve_host (LuSymbolic.refactor_solve_host)"},
-            "gpu_launches": 2 * K,
+            "gpu_launches": 2 * K,            # lu_refactor_kernel + lu_solve_kernel per step
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

@@ -563,8 +563,11 @@ int csp3_lu_refactor_solve_host(csp3_lu_symbolic *sym, int64_t batch, const doub
     auto &G = sym->stage[devid];
     const i64 n = D.n, nnzA = D.nnzA, lnz = D.lnz, unz = D.unz;
     if (!G.ready) {
-        i64 chunk = (64ll << 20) / std::max<i64>(nnzA * 8, 1);
-        chunk = std::max<i64>(64, std::min<i64>(chunk, 4096));
+        // The kernels are latency-bound: a chunk costs about the same time whether it holds 500 or 5,000
+        // systems, so chunks are as large as ~512 MB of values allows (kernels of different chunks overlap on
+        // the device, copies overlap with kernels).
+        i64 chunk = (512ll << 20) / std::max<i64>(nnzA * 8, 1);
+        chunk = std::max<i64>(256, std::min<i64>(chunk, 4096));
         chunk = (chunk + 31) & ~31ll;
         G.chunk = chunk;
         for (int s = 0; s < 3; ++s) {

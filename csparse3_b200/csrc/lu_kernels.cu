@@ -347,7 +347,11 @@ int workspace_bundle_width(i64 batch)
 {
     const int S = tuning().ws_S;
     if (S == 2 || S == 4 || S == 8 || S == 16) return S;
-    return (batch >= 16 * kNumSMs) ? 8 : 4;
+    // The kernels are latency-bound per warp: use the narrowest bundle that still lets every bundle of the
+    // batch be resident at once (32 one-warp CTAs per SM), wider only when the batch would not fit in one wave.
+    for (int w = 2; w <= 8; w *= 2)
+        if ((batch + w - 1) / w <= (i64)32 * kNumSMs) return w;
+    return 16;
 }
 
 int launch_refactor(const DevSchedule &D, i64 batch, const double *Ax, double *Lx, double *Ux, i32 *status,
@@ -368,7 +372,18 @@ int launch_refactor(const DevSchedule &D, i64 batch, const double *Ax, double *L
         set_error("factor column too long for shared memory (%d entries, bundle width %d)", len, S);
         return -1;
     }
-    int win = pow2_floor(std::max(64, tuning().rf_win > 0 ? tuning().rf_win : kCompileWindow));
+    // Recent-L ring: as large as possible while every bundle of the batch stays co-resident (one wave): a
+    // second wave costs far more than a smaller ring, because the kernel is latency- not capacity-bound.
+    int win;
+    if (tuning().rf_win > 0) {
+        win = pow2_floor(std::max(64, tuning().rf_win));
+    } else {
+        const i64 bundles = (batch + S - 1) / S;
+        const i64 per_sm = std::max<i64>(1, std::min<i64>(32, (bundles + kNumSMs - 1) / kNumSMs));
+        const size_t budget = (size_t)(227 * 1024) / (size_t)per_sm - 1024 - 256;      // per-CTA reservation + static
+        win = 1024;
+        while (win > 64 && acc_bytes + ring + (size_t)win * S * 8 > budget) win >>= 1;
+    }
     while (win > 64 && acc_bytes + ring + (size_t)win * S * 8 > kMaxSmem) win >>= 1;
     a.win_entries = win;
     const size_t smem = acc_bytes + (size_t)win * S * 8 + ring;
