@@ -373,7 +373,7 @@ int csp3_lu_sizes(const csp3_lu_symbolic *sym, int64_t out[16])
     out[0] = sym->n; out[1] = sym->nnzA; out[2] = (i64)sym->F.Li.size(); out[3] = (i64)sym->F.Ui.size();
     out[4] = sym->S.lev_refactor.nlev(); out[5] = sym->S.lev_lsolve.nlev(); out[6] = sym->S.lev_usolve.nlev();
     out[7] = sym->S.flops;
-    out[8] = (i64)(sym->S.rf_prog.bytes.size() + sym->S.ls_prog.bytes.size() + sym->S.us_prog.bytes.size());
+    out[8] = (i64)(sym->S.rf_prog.bytes.size() + sym->S.ls_prog.bytes.size() + sym->S.ur_prog.bytes.size());
     out[9] = sym->S.max_col_len;
     return 0;
 }
@@ -448,6 +448,7 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
     const size_t i_rf = add(S.rf_prog.bytes.data(), S.rf_prog.bytes.size());
     const size_t i_ls = add(S.ls_prog.bytes.data(), S.ls_prog.bytes.size());
     const size_t i_us = add(S.us_prog.bytes.data(), S.us_prog.bytes.size());
+    const size_t i_ur = add(S.ur_prog.bytes.data(), S.ur_prog.bytes.size());
     total = (total + 255) & ~(size_t)255;
     char *arena = nullptr;
     if (cudaMalloc((void **)&arena, total ? total : 256) != cudaSuccess) { set_error("lu_upload: device allocation of %zu bytes failed", total); cudaGetLastError(); return CSP3_ERR_ALLOC; }
@@ -461,7 +462,8 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
     D.rf_prog = (const uint8_t *)at(i_rf); D.rf_prog_bytes = (i32)S.rf_prog.bytes.size(); D.rf_prog_stage = S.rf_prog.stage;
     D.ls_prog = (const uint8_t *)at(i_ls); D.ls_prog_bytes = (i32)S.ls_prog.bytes.size(); D.ls_prog_stage = S.ls_prog.stage;
     D.us_prog = (const uint8_t *)at(i_us); D.us_prog_bytes = (i32)S.us_prog.bytes.size(); D.us_prog_stage = S.us_prog.stage;
-    D.ls_nslots = S.ls.nslots; D.us_nslots = S.us.nslots;
+    D.ur_prog = (const uint8_t *)at(i_ur); D.ur_prog_bytes = (i32)S.ur_prog.bytes.size(); D.ur_prog_stage = S.ur_prog.stage;
+    D.ls_nslots = S.ls.nslots; D.us_nslots = S.us.nslots; D.ur_nslots = S.ur_nslots; D.ur_max_len = S.ur_max_len;
     D.ready = true;
     return 0;
 }

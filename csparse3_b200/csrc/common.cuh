@@ -29,9 +29,10 @@ struct DevSchedule {
     bool ready = false;
     i32 n = 0, nnzA = 0, lnz = 0, unz = 0, max_col_len = 0;
     // compiled programs (program.hpp), shared by every bundle
-    const uint8_t *rf_prog = nullptr, *ls_prog = nullptr, *us_prog = nullptr;
+    const uint8_t *rf_prog = nullptr, *ls_prog = nullptr, *us_prog = nullptr, *ur_prog = nullptr;
     i32 rf_prog_bytes = 0, rf_prog_stage = 0, ls_prog_bytes = 0, ls_prog_stage = 0, us_prog_bytes = 0, us_prog_stage = 0;
-    i32 ls_nslots = 0, us_nslots = 0;
+    i32 ur_prog_bytes = 0, ur_prog_stage = 0;
+    i32 ls_nslots = 0, us_nslots = 0, ur_nslots = 0, ur_max_len = 0;
     void *arena = nullptr;             // single allocation backing all of the above
     size_t arena_bytes = 0;
 };

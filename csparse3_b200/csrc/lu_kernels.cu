@@ -163,25 +163,46 @@ __global__ void __launch_bounds__(32) lu_refactor_kernel(const RefactorArgs a)
         for (int t = e + E; t < a_cnt; t += E) acc[ps.ld<uint16_t>(po + 2 * t) * S] = __ldg(Axg + ps.ld<int>(pa + 4 * t));
         __syncwarp();
 
-        // left-looking updates, one pair record per off-diagonal entry of U(:,k), in the stored (topological) order
-        for (int pi = 0; pi < pair_cnt; ++pi) {
+        // left-looking updates, one pair record per off-diagonal entry of U(:,k), in the stored (topological) order.
+        // One-pair look-ahead: the next record's header, its first map entry and (for a far-back source column)
+        // its first L values are requested before the dependent work of the current pair starts.
+        int2 ph = make_int2(0, 0);
+        int offn = 0;
+        double lvn = 0.0;
+        if (pair_cnt > 0) {
             ps.touch(p, lane);
-            const int2 ph = ps.ld<int2>(p);
+            ph = ps.ld<int2>(p);
+            if (e < (int)((unsigned)ph.y >> 16)) {
+                offn = ps.ld<uint16_t>(p + 8 + 2 * e);
+                if (ph.x < wlo) lvn = Lg[(size_t)(ph.x + e) * LS];
+            }
+        }
+        for (int pi = 0; pi < pair_cnt; ++pi) {
             const int lstart = ph.x, moff = ph.y & 0xffff, llen = (int)((unsigned)ph.y >> 16);
             const unsigned pmap = p + 8;
             p = (pmap + 2 * llen + 7) & ~7u;
+            const int off0 = offn;
+            const double lv0 = lvn;
+            if (pi + 1 < pair_cnt) {
+                ps.touch(p, lane);
+                ph = ps.ld<int2>(p);
+                if (e < (int)((unsigned)ph.y >> 16)) {
+                    offn = ps.ld<uint16_t>(p + 8 + 2 * e);
+                    if (ph.x < wlo) lvn = Lg[(size_t)(ph.x + e) * LS];
+                }
+            }
             const double mult = acc[moff * S];
             if (lstart >= wlo) {                                             // whole source column is in the ring
-                for (int t = e; t < llen; t += E) {
+                if (e < llen) acc[off0 * S] = __dsub_rn(acc[off0 * S], __dmul_rn(win[((lstart + e) & wmask) * S], mult));
+                for (int t = e + E; t < llen; t += E) {
                     const int off = ps.ld<uint16_t>(pmap + 2 * t);
-                    const double lv = win[((lstart + t) & wmask) * S];
-                    acc[off * S] = __dsub_rn(acc[off * S], __dmul_rn(lv, mult));
+                    acc[off * S] = __dsub_rn(acc[off * S], __dmul_rn(win[((lstart + t) & wmask) * S], mult));
                 }
             } else {
-                for (int t = e; t < llen; t += E) {
+                if (e < llen) acc[off0 * S] = __dsub_rn(acc[off0 * S], __dmul_rn(lv0, mult));
+                for (int t = e + E; t < llen; t += E) {
                     const int off = ps.ld<uint16_t>(pmap + 2 * t);
-                    const double lv = Lg[(size_t)(lstart + t) * LS];
-                    acc[off * S] = __dsub_rn(acc[off * S], __dmul_rn(lv, mult));
+                    acc[off * S] = __dsub_rn(acc[off * S], __dmul_rn(Lg[(size_t)(lstart + t) * LS], mult));
                 }
             }
             __syncwarp();
@@ -214,7 +235,7 @@ __global__ void __launch_bounds__(32) lu_refactor_kernel(const RefactorArgs a)
 struct SolveArgs {
     const uint8_t *lprog, *uprog;
     i32 lprog_bytes, lprog_stage, uprog_bytes, uprog_stage;
-    i32 n, lnz, unz, nslots, ring_bytes;
+    i32 n, lnz, unz, nslots, ring_bytes, scratch_doubles;
     i64 batch;
     const double *Lx, *Ux, *b;
     double *x, *z;            // z: forward result, indexed like x; [bundle][n][S] (interleaved path only)
@@ -284,6 +305,65 @@ __device__ __forceinline__ void sweep(const SolveArgs &a, ProgStream &ps, double
     __syncwarp();
 }
 
+// Backward sweep, row-oriented: x_i = (y_i - sum_{j>i} U(i,j) x_j) / U(i,i), subtractions in descending j (the order
+// in which cs_usolve's column sweep touches row i).  The E lanes of a system fetch the row's U values and form the
+// unfused products in parallel, park them in shared memory, and lane 0 subtracts them in order.  Only the x_j that a
+// later row still needs live on chip (host-assigned slots); U is read in place from its column-major array.
+template <int S, bool IL>
+__device__ __forceinline__ void usweep_rows(const SolveArgs &a, ProgStream &ps, double *xc, double *scratch,
+                                            const double *Ug, double *park, int park_stride, double *xg,
+                                            bool valid, int lane, int e)
+{
+    constexpr int E = 32 / S;
+    constexpr int LS = IL ? S : 1;
+    const int n = a.n;
+    unsigned p = 0;
+    // operands of the row about to be processed (first chunk), requested one row ahead
+    ps.touch(p, lane);
+    int2 ha = ps.ld<int2>(p), hb = ps.ld<int2>(p + 8);
+    double un = 0.0, dn = Ug[(size_t)ha.x * LS], yn = park[(size_t)ha.y * park_stride];
+    int sn = 0;
+    if (e < (int)((unsigned)hb.x >> 16)) { const int2 en = ps.ld<int2>(p + kSvHeader + 8 * e); un = Ug[(size_t)en.x * LS]; sn = en.y & 0xffff; }
+    for (int step = 0; step < n; ++step) {
+        const int xpos = ha.y, slot_out = (int)(short)(hb.x & 0xffff), len = (int)((unsigned)hb.x >> 16);
+        const int pf_cnt = hb.y & 0xffff;
+        const int pf_x = ps.ld<int>(p + 16);
+        const unsigned pe = p + kSvHeader;                                   // entries (8 B each)
+        const unsigned ppf = pe + 8 * len;                                   // prefetch directives (i32)
+        p = (ppf + 4 * pf_cnt + 7) & ~7u;
+        const double u0 = un, d = dn, y0 = yn;
+        const int s0 = sn;
+        // prefetch directives for the row kPfCols steps ahead (its U entries, its diagonal, its parked y)
+        for (int t = e; t < pf_cnt; t += E) pf_l1(Ug + (size_t)ps.ld<int>(ppf + 4 * t) * LS);
+        if (pf_x >= 0 && e == 0) pf_l1(park + (size_t)pf_x * park_stride);
+        // look-ahead: next row's header and first-chunk operands
+        if (step + 1 < n) {
+            ps.touch(p, lane);
+            ha = ps.ld<int2>(p); hb = ps.ld<int2>(p + 8);
+            dn = Ug[(size_t)ha.x * LS];
+            yn = park[(size_t)ha.y * park_stride];
+            if (e < (int)((unsigned)hb.x >> 16)) { const int2 en = ps.ld<int2>(p + kSvHeader + 8 * e); un = Ug[(size_t)en.x * LS]; sn = en.y & 0xffff; }
+        }
+        // products of this row, parked in order
+        if (e < len) scratch[e * S] = __dmul_rn(u0, xc[s0 * S]);
+        for (int t = e + E; t < len; t += E) {
+            const int2 en = ps.ld<int2>(pe + 8 * t);
+            scratch[t * S] = __dmul_rn(Ug[(size_t)en.x * LS], xc[(en.y & 0xffff) * S]);
+        }
+        __syncwarp();
+        if (e == 0) {
+            double s = y0;
+            for (int t = 0; t < len; ++t) s = __dsub_rn(s, scratch[t * S]);
+            const double xi = s / d;
+            if (valid) xg[xpos] = xi;
+            if (slot_out >= 0) xc[slot_out * S] = xi;
+        }
+        __syncwarp();
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+}
+
 template <int S, bool IL>
 __global__ void __launch_bounds__(32) lu_solve_kernel(const SolveArgs a)
 {
@@ -303,14 +383,14 @@ __global__ void __launch_bounds__(32) lu_solve_kernel(const SolveArgs a)
     double *park = IL ? a.z + (size_t)bnd * n * S + sys : xg;
     const int park_stride = IL ? S : 1;
     double *yc = smem + sys;                                        // live row in slot s: yc[s * S]
-    uint8_t *ring = reinterpret_cast<uint8_t *>(smem + (size_t)a.nslots * S);
+    uint8_t *ring = reinterpret_cast<uint8_t *>(smem + (size_t)a.ring_bytes / 8);   // ring_bytes: byte offset of the ring
     ProgStream ps;
     // y = L \ (P b)
     ps.start(a.lprog, a.lprog_bytes, a.lprog_stage, ring, lane);
     sweep<S, IL, false>(a, ps, yc, Lg, bg, 1, park, park_stride, IL || valid, lane, sys, e);
-    // x = Q (U \ y)
+    // x = Q (U \ y), row-oriented
     ps.start(a.uprog, a.uprog_bytes, a.uprog_stage, ring, lane);
-    sweep<S, IL, true>(a, ps, yc, Ug, park, park_stride, xg, 1, valid, lane, sys, e);
+    usweep_rows<S, IL>(a, ps, yc, smem + a.scratch_doubles + sys, Ug, park, park_stride, xg, valid, lane, e);
 }
 
 template <int S, bool IL>
@@ -406,15 +486,17 @@ int launch_solve(const DevSchedule &D, i64 batch, const double *Lx, const double
     if (batch <= 0) return 0;
     SolveArgs a;
     a.lprog = D.ls_prog; a.lprog_bytes = D.ls_prog_bytes; a.lprog_stage = D.ls_prog_stage;
-    a.uprog = D.us_prog; a.uprog_bytes = D.us_prog_bytes; a.uprog_stage = D.us_prog_stage;
+    a.uprog = D.ur_prog; a.uprog_bytes = D.ur_prog_bytes; a.uprog_stage = D.ur_prog_stage;
     a.n = D.n; a.lnz = D.lnz; a.unz = D.unz;
-    a.nslots = (std::max(D.ls_nslots, D.us_nslots) + 2) & ~1;          // keeps the ring 16-byte aligned for any S
+    a.nslots = (std::max(D.ls_nslots, D.ur_nslots) + 2) & ~1;          // live rows of y (forward) / x (backward)
+    const int scratch_rows = (D.ur_max_len + 2) & ~1;                   // products of one row of U
     a.batch = batch; a.Lx = Lx; a.Ux = Ux; a.b = b; a.x = x; a.z = z;
-    const size_t ring = (size_t)kProgStages * std::max(D.ls_prog_stage, D.us_prog_stage);
-    a.ring_bytes = (i32)ring;
+    const size_t ring = (size_t)kProgStages * std::max(D.ls_prog_stage, D.ur_prog_stage);
     int S = interleaved ? workspace_bundle_width(batch) : pick_width(tuning().sv_S, batch);
-    while (!interleaved && S > 1 && (size_t)a.nslots * S * 8 + ring > kMaxSmem / 2) S >>= 1;
-    const size_t smem = (size_t)a.nslots * S * 8 + ring;
+    while (!interleaved && S > 1 && (size_t)(a.nslots + scratch_rows) * S * 8 + ring > kMaxSmem / 2) S >>= 1;
+    a.scratch_doubles = a.nslots * S;
+    a.ring_bytes = (a.nslots + scratch_rows) * S * 8;
+    const size_t smem = (size_t)a.ring_bytes + ring;
     if (smem > kMaxSmem) {
         set_error("solve working set too large for shared memory (%d live rows, bundle width %d, %zu bytes)", a.nslots, S, smem);
         return -1;

@@ -28,6 +28,17 @@
 //   +24  len x u16 slot of the updated row; pad to 8
 //        nalloc x i32 rhs index (as `rhs`), then nalloc x u16 slot; pad to 8
 //        pf_cnt x i32 rhs index of the allocations of the column kPfCols steps ahead (L1 prefetch); pad to 8
+//
+// Backward sweep, row-oriented (what the solve kernel executes for U): one record per row i, rows descending.
+// x_i = (y_i - sum_{j>i} U(i,j) x_j) / U(i,i) with the subtractions in DESCENDING j, which is exactly the order in
+// which cs_usolve's column sweep updates row i.  Only the x_j still needed by a later row are kept on chip.
+//   +0   i32  diagpos   position of U(i,i) in Ux
+//   +4   i32  xpos      q[i]: where y_i was parked by the forward sweep and where x_i goes
+//   +8   i16  slot_out  slot that receives x_i (-1: no later row needs it)      +10 u16 len
+//   +12  u16  pf_cnt    +14 reserved
+//   +16  i32  pf_x      xpos of the row kPfCols steps ahead (-1: none)           +20 reserved
+//   +24  len x { i32 pos (in Ux), u16 slot of x_j, u16 0 }   entries in descending j
+//        pf_cnt x i32   Ux positions (entries and diagonal) of the row kPfCols steps ahead; pad to 8
 #pragma once
 #include <cstdint>
 

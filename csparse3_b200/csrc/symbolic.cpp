@@ -685,7 +685,56 @@ void compile_programs(i64 n_, const std::vector<i32> &q, const Factor &F, Schedu
     };
     sweep(S.ls, true, S.ls_prog);
     sweep(S.us, false, S.us_prog);
-    (void)F;
+    // ---- row-oriented backward sweep
+    {
+        const std::vector<i32> &Up = F.Up, &Ui = F.Ui;
+        auto xpos = [&](i32 row) { return q.empty() ? row : q[row]; };
+        std::vector<i32> last_row((size_t)std::max(n, 1), -1);       // smallest row that uses x_j (-1: none)
+        for (i32 j = 0; j < n; ++j)
+            for (i32 e = Up[j]; e < Up[j + 1] - 1; ++e)
+                if (last_row[j] < 0 || Ui[e] < last_row[j]) last_row[j] = Ui[e];
+        struct RowRec { i32 diagpos, xpos, slot_out; std::vector<i32> pos, slot; };
+        std::vector<RowRec> recs((size_t)n);
+        std::vector<i32> slot_of((size_t)std::max(n, 1), -1), free_list;
+        i32 next_slot = 0;
+        S.ur_max_len = 0;
+        for (i32 i = n - 1; i >= 0; --i) {
+            RowRec &R = recs[n - 1 - i];
+            R.diagpos = Up[i + 1] - 1;
+            R.xpos = xpos(i);
+            for (i32 t = S.urow_ptr[i + 1] - 1; t >= S.urow_ptr[i]; --t) {            // descending column
+                R.pos.push_back(S.urow_pos[t]);
+                R.slot.push_back(slot_of[S.urow_col[t]]);
+            }
+            S.ur_max_len = std::max(S.ur_max_len, (i32)R.pos.size());
+            for (i32 t = S.urow_ptr[i]; t < S.urow_ptr[i + 1]; ++t) {
+                const i32 j = S.urow_col[t];
+                if (last_row[j] == i) { free_list.push_back(slot_of[j]); slot_of[j] = -1; }
+            }
+            R.slot_out = -1;
+            if (last_row[i] >= 0) {                                                   // some later row needs x_i
+                if (!free_list.empty()) { R.slot_out = free_list.back(); free_list.pop_back(); }
+                else R.slot_out = next_slot++;
+                slot_of[i] = R.slot_out;
+            }
+        }
+        S.ur_nslots = next_slot;
+        S.ur_prog = Program();
+        Emitter E(S.ur_prog.bytes);
+        for (i32 step = 0; step < n; ++step) {
+            const RowRec &R = recs[step];
+            const RowRec *Pf = step + kPfCols < n ? &recs[step + kPfCols] : nullptr;
+            const i32 pf_cnt = Pf ? (i32)Pf->pos.size() + 1 : 0;
+            E.begin();
+            E.i32v(R.diagpos); E.i32v(R.xpos);
+            E.u16v(R.slot_out); E.u16v((i32)R.pos.size()); E.u16v(pf_cnt); E.u16v(0);
+            E.i32v(Pf ? Pf->xpos : -1); E.i32v(0);
+            for (size_t t = 0; t < R.pos.size(); ++t) { E.i32v(R.pos[t]); E.u16v(R.slot[t]); E.u16v(0); }
+            if (Pf) { for (i32 v : Pf->pos) E.i32v(v); E.i32v(Pf->diagpos); }
+            E.end();
+        }
+        E.finish(S.ur_prog);
+    }
 }
 
 }  // namespace

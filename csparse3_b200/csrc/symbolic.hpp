@@ -103,7 +103,8 @@ struct Schedule {
     SolveStream ls, us;
     std::vector<i32> prow;             // prow[i] = original row r with pinv[r] == i  (y = P b: y[i] = b[prow[i]])
     // compiled programs: what the kernels actually execute (see program.hpp for the record formats)
-    Program rf_prog, ls_prog, us_prog;
+    Program rf_prog, ls_prog, us_prog, ur_prog;
+    i32 ur_nslots = 0, ur_max_len = 0;     // row-oriented backward sweep: live x values, longest row
 };
 
 // Builds the schedule; returns false (with message) when a limit is exceeded (column longer than 65535
