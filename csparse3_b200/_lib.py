@@ -39,6 +39,7 @@ SIGNATURES = {
     "csp3_spgemm_numeric_host": [i64, i64, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp],
     "csp3_spgemm_symbolic": [i64, i64, vp, vp, i64, i64, vp, vp, vp, C.POINTER(i64), vp],
     "csp3_spgemm_numeric": [i64, i64, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp],
+    "csp3_csc_plusminus_host": [i64, i64, vp, vp, vp, vp, vp, vp, f64, vp, vp, vp],
     "csp3_csc_amd": [i64, i64, i64, vp, vp, vp],
     "csp3_csc_etree": [i64, i64, vp, vp, cint, vp],
     "csp3_csc_post": [i64, vp, vp],

@@ -68,20 +68,27 @@ class CscMat:
         return str(self.todense())
 
     # ---- arithmetic -------------------------------------------------------------------------------------------
+    def _plusminus(self, other, fn):
+        assert other.m == self.m and other.n == self.n
+        na, nb = int(self.indptr[self.n]), int(other.indptr[other.n])
+        C = CscMat(m=self.m, n=self.n, nz_max=na + nb, zeros=True)
+        fn(self.m, self.n, self.indptr, self.indices[:na], self.data[:na],
+           other.indptr, other.indices[:nb], other.data[:nb], C.indptr, C.indices, C.data)
+        return C
+
     def __add__(self, other):
-        """Reference csc.py:301-323 (sptools.csc_plus_csc).  Not yet on the B200 path: SURVEY 8(f) rank 3."""
+        """Reference csc.py:301-323 (sptools.csc_plus_csc): result arrays are sized nnz(A)+nnz(B) like the
+        reference's, the valid part is indptr[n] entries."""
         if isinstance(other, CscMat):
-            raise NotImplementedError('CscMat + CscMat (csc_plus_csc) is a "next" row of the hot-path scope table '
-                                      'and is not built yet; there is no CPU fallback')
+            return self._plusminus(other, sptools.csc_plus_csc)
         if isinstance(other, (float, int)):
             raise NotImplementedError('Adding a nonzero scalar to a sparse matrix would make it a dense matrix.')
         raise NotImplementedError('Type not supported')
 
     def __sub__(self, other):
-        """Reference csc.py:325-346 (sptools.csc_minus_csc).  Same status as __add__."""
+        """Reference csc.py:325-346 (sptools.csc_minus_csc)."""
         if isinstance(other, CscMat):
-            raise NotImplementedError('CscMat - CscMat (csc_minus_csc) is a "next" row of the hot-path scope table '
-                                      'and is not built yet; there is no CPU fallback')
+            return self._plusminus(other, sptools.csc_minus_csc)
         if isinstance(other, (float, int)):
             raise NotImplementedError('Adding a non-zero scalar to a sparse matrix would make it a dense matrix.')
         raise NotImplementedError('Type not supported')

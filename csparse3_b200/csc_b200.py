@@ -141,6 +141,26 @@ class _SpTools:
             Cp[:] = np.concatenate([[0], np.cumsum(np.bincount(col, minlength=n_col))]).astype(np.int32)
 
 
+    @staticmethod
+    def _plusminus(sign, n_row, n_col, Ap, Ai, Ax, Bp, Bi, Bx, Cp, Ci, Cx):
+        Ap, Ai, Ax = as_i32(Ap, "Ap"), as_i32(Ai, "Ai"), as_f64(Ax, "Ax")
+        Bp, Bi, Bx = as_i32(Bp, "Bp"), as_i32(Bi, "Bi"), as_f64(Bx, "Bx")
+        if len(Ci) < int(Ap[n_col]) + int(Bp[n_col]) or len(Cx) < int(Ap[n_col]) + int(Bp[n_col]):
+            raise ValueError("output arrays must hold nnz(A) + nnz(B) entries")
+        check(_lib.lib().csp3_csc_plusminus_host(n_row, n_col, ptr(Ap), ptr(Ai), ptr(Ax), ptr(Bp), ptr(Bi), ptr(Bx),
+                                                 float(sign), ptr(Cp), ptr(Ci), ptr(Cx)), "csc_plus/minus_csc")
+
+    @staticmethod
+    def csc_plus_csc(n_row, n_col, Ap, Ai, Ax, Bp, Bi, Bx, Cp, Ci, Cx):
+        """C = A + B into caller-allocated arrays.  csc.h:203-210, call site csc.py:312-315."""
+        _SpTools._plusminus(1.0, n_row, n_col, Ap, Ai, Ax, Bp, Bi, Bx, Cp, Ci, Cx)
+
+    @staticmethod
+    def csc_minus_csc(n_row, n_col, Ap, Ai, Ax, Bp, Bi, Bx, Cp, Ci, Cx):
+        """C = A - B into caller-allocated arrays.  csc.h:212-219, call site csc.py:336-339."""
+        _SpTools._plusminus(-1.0, n_row, n_col, Ap, Ai, Ax, Bp, Bi, Bx, Cp, Ci, Cx)
+
+
 sptools = _SpTools()
 
 

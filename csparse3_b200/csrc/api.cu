@@ -295,6 +295,29 @@ int csp3_spgemm_numeric_host(int64_t Am, int64_t An, const int32_t *Ap, const in
     return 0;
 }
 
+// ---- A + B / A - B ---------------------------------------------------------------------------------------
+int csp3_csc_plusminus_host(int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                            const int32_t *Bp, const int32_t *Bi, const double *Bx, double sign, int32_t *Cp,
+                            int32_t *Ci, double *Cx)
+{
+    if (m < 0 || n < 0 || !Ap || !Bp || !Cp) { set_error("csc_plusminus: bad arguments"); return CSP3_ERR_ARG; }
+    if (int rc = require_device()) return rc;
+    const i64 na = Ap[n], nb = Bp[n];
+    Dev dAp, dAi, dAx, dBp, dBi, dBx, dCp, dCi, dCx;
+    CSP3_TRY(dAp.put(Ap, (size_t)(n + 1) * 4)); CSP3_TRY(dAi.put(Ai, (size_t)na * 4)); CSP3_TRY(dAx.put(Ax, (size_t)na * 8));
+    CSP3_TRY(dBp.put(Bp, (size_t)(n + 1) * 4)); CSP3_TRY(dBi.put(Bi, (size_t)nb * 4)); CSP3_TRY(dBx.put(Bx, (size_t)nb * 8));
+    CSP3_TRY(dCp.alloc((size_t)(n + 1) * 4)); CSP3_TRY(dCi.alloc((size_t)(na + nb) * 4)); CSP3_TRY(dCx.alloc((size_t)(na + nb) * 8));
+    int rc = csc_add_device(m, n, dAp.as<i32>(), dAi.as<i32>(), dAx.as<double>(), dBp.as<i32>(), dBi.as<i32>(),
+                            dBx.as<double>(), sign, dCp.as<i32>(), dCi.as<i32>(), dCx.as<double>(), nullptr);
+    if (rc) return rc;
+    CSP3_CUDA(cudaDeviceSynchronize());
+    CSP3_TRY(dCp.get(Cp, (size_t)(n + 1) * 4));
+    const i64 nc = Cp[n];
+    CSP3_TRY(dCi.get(Ci, (size_t)nc * 4));
+    CSP3_TRY(dCx.get(Cx, (size_t)nc * 8));
+    return 0;
+}
+
 // ---- host symbolic ----------------------------------------------------------------------------------------
 int csp3_csc_amd(int64_t order, int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, int32_t *q)
 {

@@ -245,6 +245,42 @@ k_spgemm_big(int ncols, const i32 *__restrict__ list, const i32 *__restrict__ Ap
     }
 }
 
+// ---- C = A + sign*B (sparsetools csr_binop_csr semantics: duplicates summed per operand, exact zeros dropped) ----
+// One thread per column.  Inputs may be unsorted and may contain duplicates (the reference tolerates both); the
+// distinct rows of a column are visited in first-touch order (A's entries, then B's), which costs O(len^2) per
+// column -- columns of the matrices on this path have a handful of entries.  Output rows are sorted.
+template <bool FILL>
+__global__ void k_csc_add(int n, const i32 *__restrict__ Ap, const i32 *__restrict__ Ai, const double *__restrict__ Ax,
+                          const i32 *__restrict__ Bp, const i32 *__restrict__ Bi, const double *__restrict__ Bx,
+                          double sign, i32 *cnt, const i32 *__restrict__ Cp, i32 *Ci, double *Cx)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int a0 = __ldg(Ap + j), a1 = __ldg(Ap + j + 1), b0 = __ldg(Bp + j), b1 = __ldg(Bp + j + 1);
+        const int la = a1 - a0, total = la + (b1 - b0);
+        int out = FILL ? __ldg(Cp + j) : 0;
+        const int base = out;
+        for (int t = 0; t < total; ++t) {
+            const int r = (t < la) ? __ldg(Ai + a0 + t) : __ldg(Bi + b0 + t - la);
+            bool seen = false;
+            for (int u = 0; u < t && !seen; ++u) seen = ((u < la) ? __ldg(Ai + a0 + u) : __ldg(Bi + b0 + u - la)) == r;
+            if (seen) continue;
+            double sa = 0.0, sb = 0.0;
+            for (int u = a0; u < a1; ++u) if (__ldg(Ai + u) == r) sa = __dadd_rn(sa, __ldg(Ax + u));
+            for (int u = b0; u < b1; ++u) if (__ldg(Bi + u) == r) sb = __dadd_rn(sb, __ldg(Bx + u));
+            const double res = (sign > 0.0) ? __dadd_rn(sa, sb) : __dsub_rn(sa, sb);
+            if (res != 0.0) {
+                if (FILL) {                       // insertion keeps the column sorted by row
+                    int q = out;
+                    while (q > base && Ci[q - 1] > r) { Ci[q] = Ci[q - 1]; Cx[q] = Cx[q - 1]; --q; }
+                    Ci[q] = r; Cx[q] = res;
+                }
+                ++out;
+            }
+        }
+        if (!FILL) cnt[j] = out;
+    }
+}
+
 inline int grid_for(i64 work, int per_block, int cap = kNumSMs * 16)
 {
     const i64 g = (work + per_block - 1) / per_block;
@@ -379,6 +415,21 @@ int spgemm_device(bool numeric, i64 Am, i64 An, const i32 *Ap, const i32 *Ai, co
         CSP3_CUDA(cudaStreamSynchronize(st));
         if (nnz_out) *nnz_out = run;
     }
+    return 0;
+}
+
+// C = A + sign*B.  Cp[n+1] is filled; Ci/Cx receive Cp[n] entries (caller capacity >= nnzA + nnzB).
+int csc_add_device(i64 m, i64 n, const i32 *Ap, const i32 *Ai, const double *Ax, const i32 *Bp, const i32 *Bi,
+                   const double *Bx, double sign, i32 *Cp, i32 *Ci, double *Cx, cudaStream_t st)
+{
+    (void)m;
+    if (n == 0) { CSP3_CUDA(cudaMemsetAsync(Cp, 0, 4, st)); return 0; }
+    DevBuf cnt(st);
+    if (cnt.alloc((size_t)(n + 1) * 4)) { set_error("device alloc failed"); return -3; }
+    k_csc_add<false><<<grid_for(n, kThreads), kThreads, 0, st>>>((int)n, Ap, Ai, Ax, Bp, Bi, Bx, sign, cnt.as<i32>(), nullptr, nullptr, nullptr);
+    k_scan<<<1, 1024, 0, st>>>((int)n, cnt.as<i32>(), Cp);
+    k_csc_add<true><<<grid_for(n, kThreads), kThreads, 0, st>>>((int)n, Ap, Ai, Ax, Bp, Bi, Bx, sign, nullptr, Cp, Ci, Cx);
+    CSP3_CUDA(cudaGetLastError());
     return 0;
 }
 

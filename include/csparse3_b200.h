@@ -93,6 +93,15 @@ int csp3_spgemm_numeric(int64_t Am, int64_t An, const int32_t *Ap, const int32_t
                         int64_t Bm, int64_t Bn, const int32_t *Bp, const int32_t *Bi, const double *Bx,
                         const int32_t *Cp, int32_t *Ci, double *Cx, void *stream);
 
+/* ---- A + B, A - B ---------------------------------------------------------------------------------------- */
+/* C = A + sign*B (sign = +1 or -1).  Replaces sptools.csc_plus_csc / csc_minus_csc, call sites
+ * src/CSparse3/csc.py:312-315, :336-339; source mirror src/sparsetools/csc.h:203-219 -> csr.h:692-908
+ * (duplicates summed per operand, exact zeros dropped).  Cp[n+1] is filled, Ci/Cx (capacity nnzA + nnzB, as the
+ * reference allocates them) receive Cp[n] entries with row indices sorted inside each column. */
+int csp3_csc_plusminus_host(int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                            const int32_t *Bp, const int32_t *Bi, const double *Bx, double sign, int32_t *Cp,
+                            int32_t *Ci, double *Cx);
+
 /* ---- host symbolic phase (runs once per pattern, cached by the caller) ---------------------------------- */
 /* q = amd(order, A): CSparse cs_amd.  order 0 natural, 1 A+A', 2 S'S (dense rows dropped), 3 A'A.  q[n]. */
 int csp3_csc_amd(int64_t order, int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, int32_t *q);

@@ -34,11 +34,15 @@ def test_reference_golden_vectors():
 
 
 def test_test1_operations_replay(golden_test1):
-    """src/test/test1_operations.py with its exact-equality criterion (A+B / A-B are not built yet)."""
+    """src/test/test1_operations.py, every operator, with its exact-equality criterion."""
     d = golden_test1
     m, n = (int(v) for v in d["Ashape"])
     A2 = CscMat(m, n, indptr=d["Ap"], indices=d["Ai"], data=d["Ax"])
     B2 = CscMat(m, n, indptr=d["Bp"], indices=d["Bi"], data=d["Bx"])
+    C2 = A2 + B2
+    assert (C2.todense() == d["scipy_ApB"]).all()
+    assert ((A2 - B2).todense() == d["scipy_AmB"]).all()
+    assert np.array_equal(C2 * d["x"], sp.csc_matrix(d["scipy_ApB"]) @ d["x"])          # G = (A + B) * x
     assert ((A2 * B2).todense() == d["scipy_AB"]).all()
     assert (A2.dot(B2).todense() == d["scipy_AB"]).all()
     assert ((A2 * d["x"]) == d["scipy_Ax"]).all()
@@ -127,6 +131,28 @@ def test_transpose_tocsr_spgemm_vs_oracle(seed):
         A2 = CscMat(m, k, indptr=Ap, indices=Ai, data=Ax); B2 = CscMat(k, n, indptr=Bp, indices=Bi, data=Bx)
         S = sp.csc_matrix((Ax, Ai, Ap), shape=(m, k)) @ sp.csc_matrix((Bx, Bi, Bp), shape=(k, n))
         assert ((A2 * B2).todense() == S.toarray()).all()
+
+
+def test_plus_minus_vs_oracle(golden_ref):
+    rng = np.random.default_rng(77)
+    cases = [(40, 30, 0.2), (1, 1, 1.0), (200, 150, 0.03), (64, 64, 0.6)]
+    mats = []
+    for m, n, dens in cases:
+        mats.append((m, n, _rand_csc(rng, m, n, dens), _rand_csc(rng, m, n, dens)))
+    d = golden_ref                                     # unsorted row indices (first-touch ordered product) vs sorted
+    mats.append((53, 53, (d["U_p"], d["U_i"], d["U_x"]), (d["Sp"], d["Si"], d["Sx"])))
+    dup_p = np.array([0, 3, 5], dtype=np.int32); dup_i = np.array([1, 0, 1, 2, 2], dtype=np.int32)       # duplicates
+    dup_x = np.array([1.0, 2.0, 3.0, 4.0, -4.0])
+    mats.append((3, 2, (dup_p, dup_i, dup_x), (dup_p, dup_i, dup_x * 0.5)))
+    for m, n, (Ap, Ai, Ax), (Bp, Bi, Bx) in mats:
+        for sign, fn in ((1.0, B.sptools.csc_plus_csc), (-1.0, B.sptools.csc_minus_csc)):
+            cap = int(Ap[n] + Bp[n])
+            Cp = np.zeros(n + 1, dtype=np.int32); Ci = np.zeros(max(cap, 1), dtype=np.int32); Cx = np.zeros(max(cap, 1))
+            Op = np.zeros(n + 1, dtype=np.int32); Oi = np.zeros(max(cap, 1), dtype=np.int32); Ox = np.zeros(max(cap, 1))
+            fn(m, n, Ap, Ai, Ax, Bp, Bi, Bx, Cp, Ci, Cx)
+            k = orc.csc_plusminus_csc(m, n, Ap, Ai, Ax, Bp, Bi, Bx, sign, Op, Oi, Ox)
+            oi, ox = sort_columns(n, Op, Oi[:k], Ox[:k])
+            assert np.array_equal(Cp, Op) and np.array_equal(Ci[:k], oi) and np.array_equal(Cx[:k], ox)
 
 
 def test_spgemm_big_columns_and_laplacian():
