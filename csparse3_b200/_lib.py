@@ -49,6 +49,7 @@ SIGNATURES = {
     "csp3_lu_sizes": [vp, C.POINTER(i64 * 16)],
     "csp3_lu_get_pattern": [vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "csp3_lu_get_levels": [vp, cint, vp, vp, vp],
+    "csp3_lu_get_program": [vp, cint, vp, i64, vp],
     "csp3_lu_upload": [vp, vp],
     "csp3_lu_refactor_batched": [vp, i64, vp, vp, vp, vp, vp],
     "csp3_lu_solve_batched": [vp, i64, vp, vp, vp, vp, vp],
@@ -61,7 +62,7 @@ SIGNATURES = {
     "csp3_lu_solve_host": [vp, i64, vp, vp, vp, vp],
     "csp3_csc_lusol_host": [i64, i64, vp, vp, vp, vp, f64],
 }
-_RESTYPE = {"csp3_last_error_string": C.c_char_p, "csp3_lu_workspace_bytes": i64}
+_RESTYPE = {"csp3_last_error_string": C.c_char_p, "csp3_lu_workspace_bytes": i64, "csp3_lu_get_program": i64}
 
 _lib = None
 

@@ -30,6 +30,9 @@ Tuning &tuning()
         auto env = [](const char *k) { const char *s = getenv(k); return s ? atoi(s) : 0; };
         v.rf_S = env("CSP3_RF_S"); v.sv_S = env("CSP3_SV_S"); v.ws_S = env("CSP3_WS_S");
         v.rf_win = env("CSP3_RF_WIN"); v.sv_stage = env("CSP3_SV_STAGE");
+        if (getenv("CSP3_WIDE")) v.wide = env("CSP3_WIDE");
+        v.wide_S = env("CSP3_WIDE_S"); v.wide_R = env("CSP3_WIDE_LANE"); v.wide_ring = env("CSP3_WIDE_R"); v.wide_stage = env("CSP3_WIDE_F");
+        v.wide_budget = env("CSP3_WIDE_BUDGET");
         return v;
     }();
     return t;
@@ -83,6 +86,7 @@ struct csp3_lu_symbolic {
     std::vector<i32> Ap, Ai, q;
     Factor F;
     Schedule S;
+    WideProgram W;                     // wide refactor program (ok == false: pattern does not fit, v3 kernels are used)
     DevSchedule dev[kMaxDevices];
     // staging for csp3_lu_refactor_solve_host (per device, lazily created)
     struct Stage {
@@ -94,6 +98,27 @@ struct csp3_lu_symbolic {
     } stage[kMaxDevices];
     std::mutex mu;
 };
+
+// Wide program: bundles of 8 systems by default.  The shared-memory budget of a bundle is chosen so that a
+// 10,000-system batch (1,250 one-warp CTAs = 8.4 per SM) is resident at once: 9 CTAs per SM; larger budgets are
+// tried for patterns with long columns (fewer resident bundles, more waves).
+static void compile_wide(csp3_lu_symbolic &Sy)
+{
+    const Tuning &t = tuning();
+    if (t.wide == 0 || Sy.n == 0) return;
+    const i32 width = (t.wide_S == 4 || t.wide_S == 16 || t.wide_S == 32) ? t.wide_S : 8;
+    const int ctas_per_sm[4] = {(10000 / width + kNumSMs - 1) / kNumSMs, 0, 0, 0};
+    for (int i = 0; i < 3; ++i) {
+        const int per_sm = std::max(1, ctas_per_sm[0] >> i);
+        const size_t budget = t.wide_budget > 0 ? (size_t)t.wide_budget
+                                                : std::min<size_t>((size_t)200 * 1024, ((size_t)228 * 1024 / per_sm - 1024) & ~(size_t)255);
+        const char *why = "";
+        const i32 per_lane = (t.wide_R == 4 && width >= 16) ? 4 : 2;
+        if (compile_wide_refactor(Sy.S, Sy.F, width, 32 * per_lane / width, budget, t.wide_ring, t.wide_stage, Sy.W, &why)) return;
+        if (t.wide_budget > 0) break;
+    }
+    Sy.W = WideProgram();
+}
 
 extern "C" {
 
@@ -357,6 +382,7 @@ int csp3_lu_analyze(int64_t order, int64_t n, const int32_t *Ap, const int32_t *
     if (st != 0) { set_error("lu_analyze: no non-zero pivot in step %d", st - 1); return st; }
     const char *why = "";
     if (!build_schedule(n, Ap, Ai, Sy->q, Sy->F, Sy->S, &why)) { set_error("lu_analyze: %s", why); return CSP3_ERR_ARG; }
+    compile_wide(*Sy);
     *sym = Sy.release();
     return 0;
 }
@@ -385,6 +411,7 @@ int csp3_lu_analyze_fixed(int64_t n, const int32_t *Ap, const int32_t *Ai, const
     }
     const char *why = "";
     if (!build_schedule(n, Ap, Ai, Sy->q, Sy->F, Sy->S, &why)) { set_error("lu_analyze_fixed: %s", why); return CSP3_ERR_ARG; }
+    compile_wide(*Sy);
     *sym = Sy.release();
     return 0;
 }
@@ -398,6 +425,8 @@ int csp3_lu_sizes(const csp3_lu_symbolic *sym, int64_t out[16])
     out[7] = sym->S.flops;
     out[8] = (i64)(sym->S.rf_prog.bytes.size() + sym->S.ls_prog.bytes.size() + sym->S.ur_prog.bytes.size());
     out[9] = sym->S.max_col_len;
+    out[10] = sym->W.ok ? sym->W.width : 0; out[11] = sym->W.ring_entries; out[12] = sym->W.stage_entries;
+    out[13] = sym->W.immediate_fetches; out[14] = sym->W.near_fma; out[15] = (i64)sym->W.smem_bytes;
     return 0;
 }
 
@@ -423,6 +452,31 @@ int csp3_lu_get_levels(const csp3_lu_symbolic *sym, int kind, int32_t *level, in
     if (order) std::memcpy(order, L.order.data(), L.order.size() * 4);
     if (lptr) std::memcpy(lptr, L.lptr.data(), L.lptr.size() * 4);
     return 0;
+}
+
+int64_t csp3_lu_get_program(const csp3_lu_symbolic *sym, int which, uint8_t *buf, int64_t capacity, int64_t geometry[8])
+{
+    if (!sym) { set_error("lu_get_program: null handle"); return CSP3_ERR_ARG; }
+    const Program *P = nullptr;
+    switch (which) {
+        case 0: P = &sym->S.rf_prog; break;
+        case 1: P = &sym->S.ls_prog; break;
+        case 2: P = &sym->S.ur_prog; break;
+        case 3: P = sym->W.ok ? &sym->W.prog : nullptr; break;
+        default: break;
+    }
+    if (!P) { set_error("lu_get_program: program %d not available", which); return CSP3_ERR_ARG; }
+    if (geometry) {
+        std::memset(geometry, 0, 8 * sizeof(int64_t));
+        geometry[0] = P->stage;
+        if (which == 3) {
+            geometry[1] = sym->W.width; geometry[2] = sym->W.acc_slots; geometry[3] = sym->W.ring_entries;
+            geometry[4] = sym->W.stage_entries; geometry[5] = sym->W.records; geometry[6] = (i64)sym->W.smem_bytes;
+            geometry[7] = sym->W.groups;
+        }
+    }
+    if (buf && capacity >= (int64_t)P->bytes.size()) std::memcpy(buf, P->bytes.data(), P->bytes.size());
+    return (int64_t)P->bytes.size();
 }
 
 static void free_stage(csp3_lu_symbolic::Stage &g)
@@ -472,6 +526,7 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
     const size_t i_ls = add(S.ls_prog.bytes.data(), S.ls_prog.bytes.size());
     const size_t i_us = add(S.us_prog.bytes.data(), S.us_prog.bytes.size());
     const size_t i_ur = add(S.ur_prog.bytes.data(), S.ur_prog.bytes.size());
+    const size_t i_wrf = add(sym->W.prog.bytes.data(), sym->W.ok ? sym->W.prog.bytes.size() : 0);
     total = (total + 255) & ~(size_t)255;
     char *arena = nullptr;
     if (cudaMalloc((void **)&arena, total ? total : 256) != cudaSuccess) { set_error("lu_upload: device allocation of %zu bytes failed", total); cudaGetLastError(); return CSP3_ERR_ALLOC; }
@@ -487,6 +542,12 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
     D.us_prog = (const uint8_t *)at(i_us); D.us_prog_bytes = (i32)S.us_prog.bytes.size(); D.us_prog_stage = S.us_prog.stage;
     D.ur_prog = (const uint8_t *)at(i_ur); D.ur_prog_bytes = (i32)S.ur_prog.bytes.size(); D.ur_prog_stage = S.ur_prog.stage;
     D.ls_nslots = S.ls.nslots; D.us_nslots = S.us.nslots; D.ur_nslots = S.ur_nslots; D.ur_max_len = S.ur_max_len;
+    if (sym->W.ok) {
+        const WideProgram &W = sym->W;
+        D.wide_ok = true; D.wide_S = W.width; D.wide_R = W.width * W.groups / 32;
+        D.wrf_prog = (const uint8_t *)at(i_wrf); D.wrf_prog_bytes = (i32)W.prog.bytes.size(); D.wrf_prog_stage = W.prog.stage;
+        D.wrf_acc_slots = W.acc_slots; D.wrf_lsrc_entries = W.ring_entries + W.stage_entries; D.wrf_smem = W.smem_bytes;
+    }
     D.ready = true;
     return 0;
 }
@@ -524,14 +585,14 @@ int csp3_lu_solve_batched(const csp3_lu_symbolic *sym, int64_t batch, const doub
 int64_t csp3_lu_workspace_bytes(const csp3_lu_symbolic *sym, int64_t batch)
 {
     if (!sym || batch < 0) return -1;
-    const i64 padded = (batch + 15) / 16 * 16;
+    const i64 padded = (batch + 31) / 32 * 32;
     return padded * (int64_t)(sym->F.Li.size() + sym->F.Ui.size() + (size_t)sym->n) * 8 + 512;
 }
 
 // workspace carve-up (bundle-interleaved): [ Lw | Uw | z ], each padded to whole bundles
 static void carve_workspace(const DevSchedule &D, i64 batch, void *work, double **Lw, double **Uw, double **z)
 {
-    const i64 padded = (batch + 15) / 16 * 16;
+    const i64 padded = (batch + 31) / 32 * 32;
     double *w = (double *)(((uintptr_t)work + 255) & ~(uintptr_t)255);
     *Lw = w; w += padded * D.lnz;
     *Uw = w; w += padded * D.unz;

@@ -33,6 +33,11 @@ struct DevSchedule {
     i32 rf_prog_bytes = 0, rf_prog_stage = 0, ls_prog_bytes = 0, ls_prog_stage = 0, us_prog_bytes = 0, us_prog_stage = 0;
     i32 ur_prog_bytes = 0, ur_prog_stage = 0;
     i32 ls_nslots = 0, us_nslots = 0, ur_nslots = 0, ur_max_len = 0;
+    // wide (lane = system) refactor program, lu_wide.cu
+    bool wide_ok = false;
+    i32 wide_S = 0, wide_R = 2, wrf_prog_bytes = 0, wrf_prog_stage = 0, wrf_acc_slots = 0, wrf_lsrc_entries = 0;
+    const uint8_t *wrf_prog = nullptr;
+    size_t wrf_smem = 0;
     void *arena = nullptr;             // single allocation backing all of the above
     size_t arena_bytes = 0;
 };
@@ -43,13 +48,17 @@ int launch_refactor(const DevSchedule &D, i64 batch, const double *Ax, double *L
                     bool interleaved, cudaStream_t st);
 int launch_solve(const DevSchedule &D, i64 batch, const double *Lx, const double *Ux, const double *b,
                  double *x, double *z, bool interleaved, cudaStream_t st);
-int workspace_bundle_width(i64 batch);
+int workspace_bundle_width(const DevSchedule &D, i64 batch);
+bool use_wide(const DevSchedule &D, i64 batch);
+int launch_refactor_wide(const DevSchedule &D, i64 batch, const double *Ax, double *Lw, double *Uw, i32 *status,
+                         cudaStream_t st);
 
 // tuning knobs (env CSP3_RF_S, CSP3_SV_S: bundle width of the system-major kernels; CSP3_WS_S: bundle width of
 // the workspace path; CSP3_RF_WIN: entries of the recent-L ring; CSP3_SV_STAGE: entries per cp.async stage;
 // 0 = automatic)
 struct Tuning {
     int rf_S = 0, sv_S = 0, ws_S = 0, rf_win = 0, sv_stage = 0;
+    int wide = 1, wide_S = 0, wide_R = 0, wide_ring = 0, wide_stage = 0, wide_budget = 0;   // CSP3_WIDE (0 disables), CSP3_WIDE_S/_R/_F/_BUDGET
 };
 Tuning &tuning();
 

@@ -423,8 +423,15 @@ int pick_width(int requested, i64 batch)
 
 }  // namespace
 
-int workspace_bundle_width(i64 batch)
+bool use_wide(const DevSchedule &D, i64 batch)
 {
+    (void)batch;
+    return D.wide_ok && tuning().wide != 0 && tuning().ws_S == 0;
+}
+
+int workspace_bundle_width(const DevSchedule &D, i64 batch)
+{
+    if (use_wide(D, batch)) return D.wide_S;
     const int S = tuning().ws_S;
     if (S == 2 || S == 4 || S == 8 || S == 16) return S;
     // The kernels are latency-bound per warp: use the narrowest bundle that still lets every bundle of the
@@ -438,11 +445,12 @@ int launch_refactor(const DevSchedule &D, i64 batch, const double *Ax, double *L
                     bool interleaved, cudaStream_t st)
 {
     if (batch <= 0) return 0;
+    if (interleaved && use_wide(D, batch)) return launch_refactor_wide(D, batch, Ax, Lx, Ux, status, st);
     RefactorArgs a;
     a.prog = D.rf_prog; a.prog_bytes = D.rf_prog_bytes; a.prog_stage = D.rf_prog_stage;
     a.n = D.n; a.nnzA = D.nnzA; a.lnz = D.lnz; a.unz = D.unz;
     a.batch = batch; a.Ax = Ax; a.Lx = Lx; a.Ux = Ux; a.status = status;
-    int S = interleaved ? workspace_bundle_width(batch) : pick_width(tuning().rf_S, batch);
+    int S = interleaved ? workspace_bundle_width(D, batch) : pick_width(tuning().rf_S, batch);
     const int len = D.max_col_len > 0 ? D.max_col_len : 1;
     const size_t ring = (size_t)kProgStages * D.rf_prog_stage;
     while (!interleaved && S > 1 && (size_t)len * S * 8 + ring > kMaxSmem / 2) S >>= 1;
@@ -492,7 +500,7 @@ int launch_solve(const DevSchedule &D, i64 batch, const double *Lx, const double
     const int scratch_rows = (D.ur_max_len + 2) & ~1;                   // products of one row of U
     a.batch = batch; a.Lx = Lx; a.Ux = Ux; a.b = b; a.x = x; a.z = z;
     const size_t ring = (size_t)kProgStages * std::max(D.ls_prog_stage, D.ur_prog_stage);
-    int S = interleaved ? workspace_bundle_width(batch) : pick_width(tuning().sv_S, batch);
+    int S = interleaved ? workspace_bundle_width(D, batch) : pick_width(tuning().sv_S, batch);
     while (!interleaved && S > 1 && (size_t)(a.nslots + scratch_rows) * S * 8 + ring > kMaxSmem / 2) S >>= 1;
     a.scratch_doubles = a.nslots * S;
     a.ring_bytes = (a.nslots + scratch_rows) * S * 8;

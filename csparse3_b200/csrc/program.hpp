@@ -51,3 +51,58 @@ constexpr int kRfHeader = 24;
 constexpr int kSvHeader = 24;
 
 }  // namespace csp3
+
+// ---------------------------------------------------------------------------------------------------------
+// "Wide" programs (lu_wide.cu): lane = system.  One warp owns a bundle of S systems (S = 16: lanes are
+// 2 entry groups x 16 systems; S = 32: one entry group), every quantity below is uniform over the systems of
+// a bundle.  Values live in bundle-interleaved arrays [entry][S], so one entry of all systems of a bundle is
+// one contiguous 8*S-byte run.
+//
+// Shared memory of a refactor warp:  acc[acc_slots][S] | lsrc[ring_entries + stage_entries][S] | program ring
+//   lsrc[0, ring_entries)        compile-time managed cache of recently finalised L columns (sequential
+//                                allocation, a column is never split by the wrap)
+//   lsrc[ring_entries, +stage)   landing area of far (not cached) source columns, fetched from the bundle's L
+//                                array with cp.async kWideLookahead records before the pair that consumes them
+// Every record issues at most one fetch and commits exactly one cp.async group, so "wait_group kWideLookahead"
+// at record r guarantees everything requested at records <= r - kWideLookahead has landed (this also covers the
+// program ring itself, whose stage loads ride in the groups of the records that trigger them).
+//
+// Records are 16-byte aligned and never straddle the end of the program ring; the reader keeps a running pointer
+// into the ring and never masks: flag bits tell it when the next record starts at the ring base (wrap) and how
+// many program stages the record enters (each entry requests one more stage).  All shared-memory positions are
+// BYTE offsets from the start of the value area (acc first, lsrc right behind it), all global positions of the
+// fetches are 16-byte units, so decoding is adds only.  EB = 8*S is the size of one bundle entry.
+//
+// Column record (48-byte header).  The first record of a program is a preamble (ucnt == 0) that only loads the
+// A values of column 0.
+//   +0   i32 up           first entry of U(:,k) in the bundle's U array
+//   +4   i32 lp           Lp[k] (the unit diagonal slot)
+//   +8   u16 ucnt         +10 u16 lcnt
+//   +12  u16 a_cnt        +14 u16 pair_cnt       (pairs with an empty source column are not emitted)
+//   +16  u16 ring         lsrc entry that receives L(1:,k); 0xffff: not cached
+//   +18  u16 an_cnt       A entries of the NEXT column that are loaded into registers while this column is
+//                         eliminated: min(a_cnt of k+1, kWideARegs * E), E = lane groups of the kernel
+//   +20  u16 fetch_dst16  +22 u16 fetch_units (16-byte units, 0: none)      +24 i32 fetch_src16
+//   +28  i32 pf_src       first A entry of the column kWidePfCols columns ahead (L2 prefetch), -1: none
+//   +32  u16 pf_cnt       +34 u8 flags (bits 1-2: stages entered, bit 3: wrap)      +35..47 reserved
+//   +48  a_cnt x u16 accumulator byte offset; pad to 4; an_cnt x i32 index into the system's Ax (next column);
+//        then the indices of this column's own entries beyond the register-held ones; pad to 16
+// Chunk record (16-byte header + C entries of 8 bytes, C = 2 * lane groups): up to C update operations
+//   acc[tgt] -= lsrc[src] * acc[mult]
+// that are mutually independent (no two share a target, no multiplier is a target of the chunk), taken in order
+// from the column's update sequence (pair after pair in the stored topological order of U(:,k), entry after
+// entry), so executing "all loads, then all stores" per chunk reproduces the sequential result bit for bit.
+// Lane group e of the kernel executes entries e and e + C/2.
+//   +0   i32 fetch_src16  +4 u16 fetch_dst16     +6 u16 fetch_units (0: none)
+//   +8   u16 flags: bit 0 = the fetch of THIS record must land before it is used (immediate),
+//                   bits 1-2 = stages entered, bit 3 = wrap                   +10..15 reserved
+//   +16  C x { u16 src_off, u16 mult_off, u16 tgt_off, u16 valid }   (byte offsets in the value area)
+// The column record's pair_cnt field counts the chunk records that follow it.
+namespace csp3 {
+constexpr int kWideLookahead = 4;     // records between a fetch and its use == pending cp.async groups allowed
+constexpr int kWideARegs = 2;         // A values (per system) a lane holds in registers one column ahead
+constexpr int kWidePfCols = 8;        // L2 prefetch distance of the A values, in columns
+constexpr int kWideColHeader = 48;
+constexpr int kWideChunkHeader = 16;
+constexpr int kWideProgStages = 8;      // ring slots of the program stream (see WideStream in lu_wide.cu)
+}  // namespace csp3

@@ -107,6 +107,23 @@ struct Schedule {
     i32 ur_nslots = 0, ur_max_len = 0;     // row-oriented backward sweep: live x values, longest row
 };
 
+// Wide (lane = system) refactor program, see program.hpp and wide_program.cpp.
+struct WideProgram {
+    bool ok = false;
+    i32 width = 0;                         // systems per bundle
+    i32 groups = 0;                        // lane groups of the kernel (entries of a column processed at once)
+    i32 acc_slots = 0, ring_entries = 0, stage_entries = 0;
+    size_t smem_bytes = 0;
+    Program prog;
+    i32 records = 0, immediate_fetches = 0;
+    i64 near_fma = 0, far_fma = 0;         // update operations whose source column is cached / fetched
+    i64 chunks = 0, chunk_ops = 0;         // chunk records and the update operations they hold
+};
+struct Factor;
+struct Schedule;
+bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 groups, size_t smem_budget,
+                           i32 ring_override, i32 stage_override, WideProgram &W, const char **why);
+
 // Builds the schedule; returns false (with message) when a limit is exceeded (column longer than 65535
 // entries or more than 2^31-1 update slots).
 bool build_schedule(i64 n, const i32 *Ap, const i32 *Ai, const std::vector<i32> &q, const Factor &F,

@@ -1,0 +1,161 @@
+"""CPU interpreter of the compiled "wide" refactor program (csparse3_b200/csrc/program.hpp), test infrastructure.
+
+Executes the byte stream record by record exactly as lu_wide.cu does -- same accumulator slots, same L cache /
+landing area, same fetch timing -- on a handful of systems at once (numpy vectors over the batch), so the host
+compiler (wide_program.cpp) can be validated against the oracle without a GPU.  cp.async is modelled at its two
+extremes: the destination is poisoned (NaN) when a fetch is issued, because the data may land at any moment from
+then on, and the data only becomes readable kWideLookahead records later (or at once for an immediate fetch).
+"""
+import ctypes as C
+import struct
+
+import numpy as np
+
+from csparse3_b200 import _lib
+
+LOOKAHEAD = 4
+AREGS = 2
+COL_HEADER = 48
+CHUNK_HEADER = 16
+PROG_STAGES = 8
+
+
+def get_program(sym, which=3):
+    geo = (C.c_int64 * 8)()
+    size = _lib.lib().csp3_lu_get_program(sym._h, which, None, 0, geo)
+    if size < 0:
+        return None, None
+    buf = np.empty(size, dtype=np.uint8)
+    _lib.lib().csp3_lu_get_program(sym._h, which, buf.ctypes.data_as(C.c_void_p), size, geo)
+    return buf.tobytes(), [int(v) for v in geo]
+
+
+def run_refactor(sym, Ax):
+    """Ax: [B, nnz] -> (Lx [B, lnz], Ux [B, unz], stats) by interpreting the wide program."""
+    prog, geo = get_program(sym, 3)
+    assert prog is not None, "wide program not available"
+    stage, width, acc_slots, ring, land, nrec, smem, groups = geo[:8]
+    EB = 8 * width
+    cover = AREGS * groups
+    ring_bytes = PROG_STAGES * stage
+    B = Ax.shape[0]
+    n, lnz, unz = sym.n, sym.lnz, sym.unz
+    nval = acc_slots + ring + land                    # value area, in entries: acc first, lsrc behind it
+    val = np.full((nval, B), np.nan)
+    Lg = np.full((lnz, B), np.nan)
+    Ug = np.full((unz, B), np.nan)
+    AxT = np.ascontiguousarray(Ax.T)
+    pending = []                       # (ready_record, dst entry, data)
+    rec_no = 0
+    p = 0
+    cur_stage = 0
+    an = None
+    fail = np.zeros(B, dtype=np.int64)
+    stats = dict(fetches=0, immediates=0, records=0)
+
+    def entry_of(byte_off):
+        assert byte_off % EB == 0
+        return byte_off // EB
+
+    def advance(p0, nbytes, flags):
+        """checks the span of the record at p0 and the stage / wrap flags; returns the offset of the next record"""
+        nonlocal cur_stage
+        assert p0 % 16 == 0
+        assert p0 // ring_bytes == (p0 + nbytes - 1) // ring_bytes, "record straddles the program ring"
+        assert nbytes <= stage, "record larger than a stage"
+        adv = (flags >> 1) & 3
+        assert p0 // stage == cur_stage + adv, "stage flags wrong"
+        cur_stage += adv
+        nxt = p0 + nbytes
+        if flags & 8:
+            nxt = (nxt + ring_bytes - 1) // ring_bytes * ring_bytes
+        return nxt
+
+    def issue(units, dst16, src16, immediate):
+        nonlocal pending
+        if units == 0:
+            return
+        flen, fdst, fsrc = entry_of(units * 16), entry_of(dst16 * 16), entry_of(src16 * 16)
+        assert fdst >= acc_slots + ring and fdst + flen <= nval, "fetch outside the landing area"
+        data = Lg[fsrc:fsrc + flen].copy()
+        assert not np.isnan(data).any(), "fetch of an L column that is not final yet"
+        val[fdst:fdst + flen] = np.nan
+        pending.append((rec_no if immediate else rec_no + LOOKAHEAD, fdst, data))
+        stats["fetches"] += 1
+        stats["immediates"] += int(immediate)
+
+    def land_ready():
+        nonlocal pending
+        keep = []
+        for ready, dst, data in pending:
+            if ready <= rec_no:
+                val[dst:dst + len(data)] = data
+            else:
+                keep.append((ready, dst, data))
+        pending = keep
+
+    for c in range(n + 1):
+        (up, lp, ucnt, lcnt, a_cnt, pair_cnt, ringpos, an_cnt, fdst16, funits, fsrc16, pf_src, pf_cnt, flags) = \
+            struct.unpack_from("<iiHHHHHHHHiiHB", prog, p)
+        so = p + COL_HEADER
+        no = p + ((COL_HEADER + 2 * a_cnt + 3) & ~3)
+        over = max(0, a_cnt - cover)
+        nbytes = (((COL_HEADER + 2 * a_cnt + 3) & ~3) + 4 * (an_cnt + over) + 15) & ~15
+        slots = [entry_of(int(v)) for v in np.frombuffer(prog, dtype=np.uint16, count=a_cnt, offset=so)]
+        srcs = np.frombuffer(prog, dtype=np.int32, count=an_cnt + over, offset=no)
+        p = advance(p, nbytes, flags)
+        issue(funits, fdst16, fsrc16, False)
+        land_ready()
+        ln = ucnt + lcnt - 1
+        assert ln <= acc_slots
+        val[:ln] = 0.0
+        if c == 0:
+            assert ucnt == 0 and a_cnt == 0 and pair_cnt == 0
+        k = c - 1
+        # scatter: register-held values first, then this column's own overflow entries
+        for t in range(a_cnt):
+            assert slots[t] < ln
+            if t < cover:
+                val[slots[t]] = an[t]
+            else:
+                val[slots[t]] = AxT[srcs[an_cnt + t - cover]]
+        an = [AxT[srcs[t]].copy() for t in range(an_cnt)]
+        if pf_src >= 0:
+            assert 0 <= pf_src and pf_src + pf_cnt <= sym.nnz
+        rec_no += 1
+        cap = 2 * groups
+        for _ in range(pair_cnt):                      # chunk records of this column
+            fsrc16, fdst16, funits, flags = struct.unpack_from("<iHHH", prog, p)
+            nbytes = CHUNK_HEADER + 8 * cap
+            ent = np.frombuffer(prog, dtype=np.uint16, count=4 * cap, offset=p + CHUNK_HEADER).reshape(cap, 4)
+            p = advance(p, nbytes, flags)
+            issue(funits, fdst16, fsrc16, bool(flags & 1))
+            land_ready()
+            ok = ent[:, 3] != 0
+            assert ok.any() and set(np.unique(ent[:, 3]).tolist()) <= {0, 1}
+            src = np.array([entry_of(int(v)) for v in ent[ok, 0]])
+            mul = np.array([entry_of(int(v)) for v in ent[ok, 1]])
+            tgt = np.array([entry_of(int(v)) for v in ent[ok, 2]])
+            assert (src >= acc_slots).all() and (mul < ucnt).all() and (tgt < ln).all()
+            assert len(set(tgt.tolist())) == len(tgt), "two operations of a chunk share a target"
+            assert not (set(mul.tolist()) & set(tgt.tolist())), "a multiplier is modified inside its chunk"
+            lv = val[src]
+            assert not np.isnan(lv).any(), "chunk reads a source that has not landed (record %d)" % rec_no
+            val[tgt] = val[tgt] - lv * val[mul]         # all loads, then all stores
+            stats["ops"] = stats.get("ops", 0) + int(ok.sum())
+            rec_no += 1
+        if ucnt > 0:
+            pivot = val[ucnt - 1].copy()
+            Ug[up:up + ucnt] = val[:ucnt]
+            Lg[lp] = 1.0
+            with np.errstate(all="ignore"):
+                v = val[ucnt:ucnt + lcnt - 1] / pivot
+            Lg[lp + 1:lp + lcnt] = v
+            if ringpos != 0xffff:
+                assert ringpos + lcnt - 1 <= ring
+                val[acc_slots + ringpos:acc_slots + ringpos + lcnt - 1] = v
+            bad = ~((np.abs(pivot) > 0) & np.isfinite(pivot))
+            fail = np.where((fail == 0) & bad, k + 1, fail)
+    stats["records"] = rec_no
+    assert rec_no == nrec
+    return np.ascontiguousarray(Lg.T), np.ascontiguousarray(Ug.T), fail, stats
