@@ -31,6 +31,7 @@ Tuning &tuning()
         v.rf_S = env("CSP3_RF_S"); v.sv_S = env("CSP3_SV_S"); v.ws_S = env("CSP3_WS_S");
         v.rf_win = env("CSP3_RF_WIN"); v.sv_stage = env("CSP3_SV_STAGE");
         if (getenv("CSP3_WIDE")) v.wide = env("CSP3_WIDE");
+        if (getenv("CSP3_WIDE_SOLVE")) v.wide_solve = env("CSP3_WIDE_SOLVE");
         v.wide_S = env("CSP3_WIDE_S"); v.wide_R = env("CSP3_WIDE_LANE"); v.wide_ring = env("CSP3_WIDE_R"); v.wide_stage = env("CSP3_WIDE_F");
         v.wide_budget = env("CSP3_WIDE_BUDGET");
         return v;
@@ -87,6 +88,8 @@ struct csp3_lu_symbolic {
     Factor F;
     Schedule S;
     WideProgram W;                     // wide refactor program (ok == false: pattern does not fit, v3 kernels are used)
+    WideSweep WF, WB;                  // wide forward / backward sweep programs
+    std::vector<i32> qinv;             // x[c] = x_pivot_order[qinv[c]]
     DevSchedule dev[kMaxDevices];
     // staging for csp3_lu_refactor_solve_host (per device, lazily created)
     struct Stage {
@@ -114,7 +117,18 @@ static void compile_wide(csp3_lu_symbolic &Sy)
                                                 : std::min<size_t>((size_t)200 * 1024, ((size_t)228 * 1024 / per_sm - 1024) & ~(size_t)255);
         const char *why = "";
         const i32 per_lane = (t.wide_R == 4 && width >= 16) ? 4 : 2;
-        if (compile_wide_refactor(Sy.S, Sy.F, width, 32 * per_lane / width, budget, t.wide_ring, t.wide_stage, Sy.W, &why)) return;
+        if (compile_wide_refactor(Sy.S, Sy.F, width, 32 * per_lane / width, budget, t.wide_ring, t.wide_stage, Sy.W, &why)) {
+            if (!compile_wide_sweep(Sy.F, true, width, Sy.W.groups, budget, Sy.WF, &why) ||
+                !compile_wide_sweep(Sy.F, false, width, Sy.W.groups, budget, Sy.WB, &why) ||
+                std::max(Sy.WF.smem_bytes, Sy.WB.smem_bytes) > (size_t)200 * 1024) {
+                if (getenv("CSP3_DEBUG")) fprintf(stderr, "csp3: wide sweeps unavailable: %s\n", why);
+                Sy.WF = WideSweep(); Sy.WB = WideSweep();
+            }
+            Sy.qinv.assign((size_t)Sy.n, 0);
+            for (i64 i = 0; i < Sy.n; ++i) Sy.qinv[(size_t)(Sy.q.empty() ? i : Sy.q[(size_t)i])] = (i32)i;
+            return;
+        }
+        if (getenv("CSP3_DEBUG")) fprintf(stderr, "csp3: wide refactor unavailable at budget %zu: %s\n", budget, why);
         if (t.wide_budget > 0) break;
     }
     Sy.W = WideProgram();
@@ -463,6 +477,8 @@ int64_t csp3_lu_get_program(const csp3_lu_symbolic *sym, int which, uint8_t *buf
         case 1: P = &sym->S.ls_prog; break;
         case 2: P = &sym->S.ur_prog; break;
         case 3: P = sym->W.ok ? &sym->W.prog : nullptr; break;
+        case 4: P = sym->WF.ok ? &sym->WF.prog : nullptr; break;
+        case 5: P = sym->WB.ok ? &sym->WB.prog : nullptr; break;
         default: break;
     }
     if (!P) { set_error("lu_get_program: program %d not available", which); return CSP3_ERR_ARG; }
@@ -473,6 +489,11 @@ int64_t csp3_lu_get_program(const csp3_lu_symbolic *sym, int which, uint8_t *buf
             geometry[1] = sym->W.width; geometry[2] = sym->W.acc_slots; geometry[3] = sym->W.ring_entries;
             geometry[4] = sym->W.stage_entries; geometry[5] = sym->W.records; geometry[6] = (i64)sym->W.smem_bytes;
             geometry[7] = sym->W.groups;
+        }
+        if (which == 4 || which == 5) {
+            const WideSweep &Wsw = which == 4 ? sym->WF : sym->WB;
+            geometry[1] = Wsw.width; geometry[2] = Wsw.nslots; geometry[3] = Wsw.landing_entries; geometry[5] = Wsw.records;
+            geometry[6] = (i64)Wsw.smem_bytes; geometry[7] = Wsw.groups;
         }
     }
     if (buf && capacity >= (int64_t)P->bytes.size()) std::memcpy(buf, P->bytes.data(), P->bytes.size());
@@ -527,6 +548,11 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
     const size_t i_us = add(S.us_prog.bytes.data(), S.us_prog.bytes.size());
     const size_t i_ur = add(S.ur_prog.bytes.data(), S.ur_prog.bytes.size());
     const size_t i_wrf = add(sym->W.prog.bytes.data(), sym->W.ok ? sym->W.prog.bytes.size() : 0);
+    const bool wsolve = sym->W.ok && sym->WF.ok && sym->WB.ok;
+    const size_t i_wfs = add(sym->WF.prog.bytes.data(), wsolve ? sym->WF.prog.bytes.size() : 0);
+    const size_t i_wbs = add(sym->WB.prog.bytes.data(), wsolve ? sym->WB.prog.bytes.size() : 0);
+    const size_t i_pinv = add(F.pinv.data(), wsolve ? F.pinv.size() * 4 : 0);
+    const size_t i_qinv = add(sym->qinv.data(), wsolve ? sym->qinv.size() * 4 : 0);
     total = (total + 255) & ~(size_t)255;
     char *arena = nullptr;
     if (cudaMalloc((void **)&arena, total ? total : 256) != cudaSuccess) { set_error("lu_upload: device allocation of %zu bytes failed", total); cudaGetLastError(); return CSP3_ERR_ALLOC; }
@@ -547,6 +573,14 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
         D.wide_ok = true; D.wide_S = W.width; D.wide_R = W.width * W.groups / 32;
         D.wrf_prog = (const uint8_t *)at(i_wrf); D.wrf_prog_bytes = (i32)W.prog.bytes.size(); D.wrf_prog_stage = W.prog.stage;
         D.wrf_acc_slots = W.acc_slots; D.wrf_lsrc_entries = W.ring_entries + W.stage_entries; D.wrf_smem = W.smem_bytes;
+        if (wsolve) {
+            D.wide_solve_ok = true;
+            D.wfs_prog = (const uint8_t *)at(i_wfs); D.wfs_prog_bytes = (i32)sym->WF.prog.bytes.size(); D.wfs_prog_stage = sym->WF.prog.stage;
+            D.wfs_records = sym->WF.records; D.wfs_nslots = sym->WF.nslots; D.wfs_smem = sym->WF.smem_bytes;
+            D.wbs_prog = (const uint8_t *)at(i_wbs); D.wbs_prog_bytes = (i32)sym->WB.prog.bytes.size(); D.wbs_prog_stage = sym->WB.prog.stage;
+            D.wbs_records = sym->WB.records; D.wbs_nslots = sym->WB.nslots; D.wbs_smem = sym->WB.smem_bytes;
+            D.d_pinv = (const i32 *)at(i_pinv); D.d_qinv = (const i32 *)at(i_qinv);
+        }
     }
     D.ready = true;
     return 0;
@@ -586,7 +620,7 @@ int64_t csp3_lu_workspace_bytes(const csp3_lu_symbolic *sym, int64_t batch)
 {
     if (!sym || batch < 0) return -1;
     const i64 padded = (batch + 31) / 32 * 32;
-    return padded * (int64_t)(sym->F.Li.size() + sym->F.Ui.size() + (size_t)sym->n) * 8 + 512;
+    return padded * (int64_t)(sym->F.Li.size() + sym->F.Ui.size() + 2 * (size_t)sym->n) * 8 + 512;
 }
 
 // workspace carve-up (bundle-interleaved): [ Lw | Uw | z ], each padded to whole bundles

@@ -38,6 +38,13 @@ struct DevSchedule {
     i32 wide_S = 0, wide_R = 2, wrf_prog_bytes = 0, wrf_prog_stage = 0, wrf_acc_slots = 0, wrf_lsrc_entries = 0;
     const uint8_t *wrf_prog = nullptr;
     size_t wrf_smem = 0;
+    // wide triangular sweeps (forward / backward)
+    bool wide_solve_ok = false;
+    const uint8_t *wfs_prog = nullptr, *wbs_prog = nullptr;
+    i32 wfs_prog_bytes = 0, wfs_prog_stage = 0, wfs_records = 0, wfs_nslots = 0;
+    i32 wbs_prog_bytes = 0, wbs_prog_stage = 0, wbs_records = 0, wbs_nslots = 0;
+    size_t wfs_smem = 0, wbs_smem = 0;
+    const i32 *d_pinv = nullptr, *d_qinv = nullptr;
     void *arena = nullptr;             // single allocation backing all of the above
     size_t arena_bytes = 0;
 };
@@ -46,19 +53,22 @@ struct DevSchedule {
 // interleaved == true: Lx/Ux/z point into a workspace in bundle-interleaved layout (see lu_kernels.cu).
 int launch_refactor(const DevSchedule &D, i64 batch, const double *Ax, double *Lx, double *Ux, i32 *status,
                     bool interleaved, cudaStream_t st);
+// z: interleaved scratch of 2 * n doubles per (padded) system
 int launch_solve(const DevSchedule &D, i64 batch, const double *Lx, const double *Ux, const double *b,
                  double *x, double *z, bool interleaved, cudaStream_t st);
 int workspace_bundle_width(const DevSchedule &D, i64 batch);
 bool use_wide(const DevSchedule &D, i64 batch);
 int launch_refactor_wide(const DevSchedule &D, i64 batch, const double *Ax, double *Lw, double *Uw, i32 *status,
                          cudaStream_t st);
+int launch_solve_wide(const DevSchedule &D, i64 batch, const double *Lw, const double *Uw, const double *b, double *x,
+                      double *z1, double *z2, cudaStream_t st);
 
 // tuning knobs (env CSP3_RF_S, CSP3_SV_S: bundle width of the system-major kernels; CSP3_WS_S: bundle width of
 // the workspace path; CSP3_RF_WIN: entries of the recent-L ring; CSP3_SV_STAGE: entries per cp.async stage;
 // 0 = automatic)
 struct Tuning {
     int rf_S = 0, sv_S = 0, ws_S = 0, rf_win = 0, sv_stage = 0;
-    int wide = 1, wide_S = 0, wide_R = 0, wide_ring = 0, wide_stage = 0, wide_budget = 0;   // CSP3_WIDE (0 disables), CSP3_WIDE_S/_R/_F/_BUDGET
+    int wide = 1, wide_solve = 1, wide_S = 0, wide_R = 0, wide_ring = 0, wide_stage = 0, wide_budget = 0;   // CSP3_WIDE (0 disables), CSP3_WIDE_S/_R/_F/_BUDGET
 };
 Tuning &tuning();
 

@@ -492,6 +492,10 @@ int launch_solve(const DevSchedule &D, i64 batch, const double *Lx, const double
                  double *x, double *z, bool interleaved, cudaStream_t st)
 {
     if (batch <= 0) return 0;
+    if (interleaved && use_wide(D, batch) && D.wide_solve_ok && tuning().wide_solve != 0) {
+        const i64 padded = (batch + 31) / 32 * 32;
+        return launch_solve_wide(D, batch, Lx, Ux, b, x, z, z + padded * D.n, st);
+    }
     SolveArgs a;
     a.lprog = D.ls_prog; a.lprog_bytes = D.ls_prog_bytes; a.lprog_stage = D.ls_prog_stage;
     a.uprog = D.ur_prog; a.uprog_bytes = D.ur_prog_bytes; a.uprog_stage = D.ur_prog_stage;

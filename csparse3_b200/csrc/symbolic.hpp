@@ -124,6 +124,16 @@ struct Schedule;
 bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 groups, size_t smem_budget,
                            i32 ring_override, i32 stage_override, WideProgram &W, const char **why);
 
+// Wide triangular sweep program (program.hpp, wide_solve.cpp)
+struct WideSweep {
+    bool ok = false;
+    i32 width = 0, groups = 0, nslots = 0, landing_entries = 0, records = 0;
+    size_t smem_bytes = 0;
+    i64 ops = 0;
+    Program prog;
+};
+bool compile_wide_sweep(const Factor &F, bool lower, i32 width, i32 groups, size_t smem_budget, WideSweep &W, const char **why);
+
 // Builds the schedule; returns false (with message) when a limit is exceeded (column longer than 65535
 // entries or more than 2^31-1 update slots).
 bool build_schedule(i64 n, const i32 *Ap, const i32 *Ai, const std::vector<i32> &q, const Factor &F,

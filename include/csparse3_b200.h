@@ -136,9 +136,10 @@ int csp3_lu_get_pattern(const csp3_lu_symbolic *sym, int32_t *q, int32_t *pinv, 
 /* Level sets.  kind 0 refactor (from U), 1 L-solve, 2 U-solve.  level[n], order[n], lptr[nlev+1]. */
 int csp3_lu_get_levels(const csp3_lu_symbolic *sym, int kind, int32_t *level, int32_t *order, int32_t *lptr);
 /* Introspection of the compiled device programs (csparse3_b200/csrc/program.hpp): which = 0 refactor, 1 forward
- * sweep, 2 backward sweep (row-oriented), 3 wide refactor.  Returns the size in bytes (copied into buf when
+ * sweep, 2 backward sweep (row-oriented), 3 wide refactor, 4 / 5 wide forward / backward sweep.  Returns the size in bytes (copied into buf when
  * capacity allows), or a negative error.  geometry (optional, 8 values): [0] stage bytes; wide refactor only:
  * [1] bundle width, [2] accumulator slots, [3] L cache entries, [4] landing entries, [5] records, [6] smem bytes,
+ * [7] lane groups; wide sweeps: [1] bundle width, [2] slots, [3] landing entries, [5] records, [6] smem bytes,
  * [7] lane groups. */
 int64_t csp3_lu_get_program(const csp3_lu_symbolic *sym, int which, uint8_t *buf, int64_t capacity,
                             int64_t geometry[8]);

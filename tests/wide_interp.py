@@ -159,3 +159,109 @@ def run_refactor(sym, Ax):
     stats["records"] = rec_no
     assert rec_no == nrec
     return np.ascontiguousarray(Lg.T), np.ascontiguousarray(Ug.T), fail, stats
+
+
+SWEEP_LOOKAHEAD = 3
+SWEEP_STAGES = 7
+
+
+def _run_sweep(sym, which, Fx, zin):
+    """Interprets one sweep program.  Fx: [B, lnz|unz] factor values, zin: [n, B] right-hand sides -> zout [n, B]."""
+    prog, geo = get_program(sym, which)
+    assert prog is not None, "wide sweep program not available"
+    stage, width, nslots, landing, _, nrec, smem, E = geo[:8]
+    EB = 8 * width
+    LA, NL = SWEEP_LOOKAHEAD, SWEEP_LOOKAHEAD + 1
+    SET = landing // NL
+    assert SET in (2 * E, 3 * E)
+    RB = 16 + 36 * E
+    ring_bytes = SWEEP_STAGES * stage
+    n = sym.n
+    B = zin.shape[1]
+    FT = np.ascontiguousarray(Fx.T)
+    slots = np.full((nslots, B), np.nan)
+    land = np.full((landing, B), np.nan)
+    zout = np.full((n, B), np.nan)
+    pending = []                                   # (ready record, kind, dst, data)
+    p = 0
+    cur_stage = 0
+    nops = 0
+    for r in range(nrec):
+        flags, = struct.unpack_from("<H", prog, p)
+        assert p % 16 == 0 and p // ring_bytes == (p + RB - 1) // ring_bytes, "record straddles the program ring"
+        adv = (flags >> 1) & 3
+        assert p // stage == cur_stage + adv, "stage flags wrong"
+        cur_stage += adv
+        loads = np.frombuffer(prog, dtype=np.int32, count=2 * E, offset=p + 16).reshape(E, 2)
+        pf = np.frombuffer(prog, dtype=np.int32, count=2 * E, offset=p + 16 + 8 * E)
+        pfd = np.frombuffer(prog, dtype=np.int32, count=E, offset=p + 16 + 16 * E)
+        fins = np.frombuffer(prog, dtype=np.int32, count=2 * E, offset=p + 16 + 20 * E).reshape(E, 2)
+        upds = np.frombuffer(prog, dtype=np.uint16, count=4 * E, offset=p + 16 + 28 * E).reshape(2 * E, 2)
+        cyc, pset = r % NL, (r + LA) % NL
+        # issue: loads into slots, gathers into the landing set of record r + LA (poisoned until they land)
+        for e in range(E):
+            gidx, w = int(loads[e, 0]), int(loads[e, 1])
+            if gidx >= 0:
+                so = (w & 0xffff)
+                assert so % EB == 0 and so // EB < nslots
+                slots[so // EB] = np.nan
+                pending.append((r + LA, 0, so // EB, zin[gidx].copy()))
+        for u in range(2 * E):
+            if pf[u] >= 0:
+                land[pset * SET + u] = np.nan
+                pending.append((r + LA, 1, pset * SET + u, FT[pf[u]].copy()))
+        for e in range(E):
+            if pfd[e] >= 0:
+                assert SET == 3 * E
+                land[pset * SET + 2 * E + e] = np.nan
+                pending.append((r + LA, 1, pset * SET + 2 * E + e, FT[pfd[e]].copy()))
+        keep = []
+        for ready, kind, dst, data in pending:
+            if ready <= r:
+                (slots if kind == 0 else land)[dst] = data
+            else:
+                keep.append((ready, kind, dst, data))
+        pending = keep
+        # finalisations
+        for e in range(E):
+            out, w = int(fins[e, 0]), int(fins[e, 1])
+            if out >= 0:
+                so, div = (w & 0xffff) // EB, (w >> 16) & 0xffff
+                v = slots[so].copy()
+                assert not np.isnan(v).any(), "finalisation of a row that has not landed (record %d)" % r
+                if div:
+                    d = land[cyc * SET + 2 * E + e]
+                    assert not np.isnan(d).any()
+                    v = v / d
+                    slots[so] = v
+                zout[out] = v
+        # updates: all loads, then all stores
+        ok = upds[:, 1] != 0xffff
+        if ok.any():
+            idx = np.nonzero(ok)[0]
+            mul = upds[idx, 0].astype(np.int64) // EB
+            tgt = upds[idx, 1].astype(np.int64) // EB
+            assert len(set(tgt.tolist())) == len(tgt) and not (set(tgt.tolist()) & set(mul.tolist()))
+            lv = land[cyc * SET + idx]
+            assert not np.isnan(lv).any() and not np.isnan(slots[mul]).any() and not np.isnan(slots[tgt]).any(), \
+                "update reads a value that has not landed (record %d)" % r
+            slots[tgt] = slots[tgt] - lv * slots[mul]
+            nops += len(idx)
+        p += RB
+        if flags & 8:
+            p = (p + ring_bytes - 1) // ring_bytes * ring_bytes
+    assert not np.isnan(zout).any()
+    return zout, nops
+
+
+def run_solve(sym, Lx, Ux, b):
+    """b: [B, n] -> x [B, n] by interpreting the forward and backward sweep programs on factors Lx, Ux."""
+    n = sym.n
+    z1 = np.empty((n, b.shape[0]))
+    z1[sym.pinv] = b.T                           # y = P b
+    z2, nf = _run_sweep(sym, 4, Lx, z1)
+    z3, nb = _run_sweep(sym, 5, Ux, z2)
+    x = np.empty((n, b.shape[0]))
+    x[sym.q] = z3                                # x[q[i]] = z[i]
+    assert nf == sym.lnz - n and nb == sym.unz - n
+    return np.ascontiguousarray(x.T)
