@@ -274,7 +274,10 @@ def main():
         peak, peak_src = peaks()
         bytes_rf = (8 * sym.nnz + 8 * sym.nnz_lu) * B          # read A, write L+U
         bytes_sv = (8 * sym.nnz_lu + 16 * n) * B               # read L+U, read b, write x
-        dom = ("lu_refactor_kernel", bytes_rf, rf_ms) if rf_ms >= sv_ms else ("lu_solve_kernel", bytes_sv, sv_ms)
+        wide = sym.wide_width > 0 and os.environ.get("CSP3_WIDE", "1") != "0"
+        rf_name = "lu_refactor_wide_kernel" if wide else "lu_refactor_kernel"
+        sv_name = "lu_sweep_wide_kernel" if wide else "lu_solve_kernel"
+        dom = (rf_name, bytes_rf, rf_ms) if rf_ms >= sv_ms else (sv_name, bytes_sv, sv_ms)
         achieved = dom[1] / (dom[2] * 1e-3) / 1e9
         step_bytes = sym.bytes_per_system() * B
         traffic = None
@@ -296,7 +299,9 @@ def main():
                        "refactor_flops_per_system": sym.flops, "levels": sym.nlev_refactor,
                        "l2": "inputs larger than L2 (%.2f GB of values per step, nothing reused across steps)" % (step_bytes / 1e9),
                        "parallelism": "batch-sharded x%d, no data-path collective" % world,
-                       "kernel_ms": {"lu_refactor_kernel": rf_ms, "lu_solve_kernel": sv_ms},
+                       "kernel_ms": {rf_name: rf_ms,
+                                     (sv_name + " x2 + rhs_to_bundles_kernel + bundles_to_x_kernel") if wide else sv_name: sv_ms},
+                       "bundle": ("%d systems per warp, 2 per lane" % sym.wide_width) if wide else "v3 kernels",
                        "bytes_per_system": sym.bytes_per_system(),
                        "step_roofline_frac": step_bytes / (total_ms / K * 1e-3) / 1e9 / peak,
                        "result_gather_ms": gather_ms},
@@ -306,7 +311,8 @@ def main():
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(B * (sym.nnz + n) * 8), "d2h_bytes_per_step": int(B * (n * 8 + 4)),
                     "ms_per_step": e2e_ms, "api": "csp3_lu_refactor_solve_host (LuSymbolic.refactor_solve_host)"},
-            "gpu_launches": 2 * K,            # lu_refactor_kernel + lu_solve_kernel per step
+            # wide path: refactor + (transpose in, forward sweep, backward sweep, transpose out); v3: refactor + solve
+            "gpu_launches": (5 if wide else 2) * K,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

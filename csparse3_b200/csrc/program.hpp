@@ -114,20 +114,21 @@ constexpr int kWideProgStages = 8;      // ring slots of the program stream (see
 //
 // Fixed-size records, E = lane groups of the kernel:
 //   +0    16-byte header: u16 flags (bits 1-2 stages entered, bit 3 wrap), rest reserved
-//   +16   E  x { i32 gidx, u16 slot_off, u16 0 }              right-hand-side loads: slot <- zin[gidx]   (gidx < 0: none)
-//   +..   2E x i32                                           factor entries the update operations of the record
+//   +16   E/2 x { i32 gidx, u16 slot_off, u16 0 }            right-hand-side loads: slot <- zin[gidx]   (gidx < 0: none)
+//   +..   2E  x i32                                          factor entries the update operations of the record
 //                                                            kSweepLookahead records AHEAD will read (< 0: none)
-//   +..   E  x i32                                           divisors (factor entries) of that record's finalisations
-//   +..   E  x { i32 out_idx, u16 slot_off, u16 divide }     finalisations: [slot /= divisor;] zout[out_idx] <- slot
+//   +..   E/2 x i32                                          divisors (factor entries) of that record's finalisations
+//   +..   E/2 x { i32 out_idx, u16 slot_off, u16 divide }    finalisations: [slot /= divisor;] zout[out_idx] <- slot
 //                                                            (out_idx < 0: none)
-//   +..   2E x { u16 mult_off, u16 tgt_off }                 updates: slot[tgt] -= value * slot[mult]
+//   +..   2E  x { u16 mult_off, u16 tgt_off }                updates: slot[tgt] -= value * slot[mult]
 //                                                            (tgt_off == 0xffff: none)
+// (224 bytes for E = 8: two records per 512-byte program stage)
 // Factor values are gathered with cp.async into a landing area of kSweepLookahead + 1 record-sized sets (2E update
-// values, then E divisors in the backward sweep), record r uses set r mod (kSweepLookahead + 1).  Right-hand sides
+// values, then E/2 divisors in the backward sweep), record r uses set r mod (kSweepLookahead + 1).  Right-hand sides
 // are copied straight into their slot at least kSweepLookahead records before the first operation that touches it.
 namespace csp3 {
 constexpr int kSweepLookahead = 3;      // records between a gather / load and its use in the sweep kernels
-constexpr int kSweepProgStages = 7;     // ring slots of the sweep program stream
+constexpr int kSweepProgStages = 6;     // ring slots of the sweep program stream
 constexpr int kWideSolveHeader = 16;
-inline constexpr int wide_solve_record_bytes(int groups) { return kWideSolveHeader + groups * (8 + 8 + 4 + 8 + 8); }
+inline constexpr int wide_solve_record_bytes(int groups) { return kWideSolveHeader + groups * (4 + 8 + 2 + 4 + 8); }
 }  // namespace csp3

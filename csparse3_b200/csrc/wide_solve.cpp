@@ -33,7 +33,7 @@ static bool compile_sweep_window(const Factor &F, bool lower, i32 width, i32 gro
     W = WideSweep();
     const i32 n = (i32)F.Lp.size() - 1;
     const std::vector<i32> &Gp = lower ? F.Lp : F.Up, &Gi = lower ? F.Li : F.Ui;
-    const i32 E = groups, cap_u = 2 * groups, LA = kSweepLookahead;
+    const i32 E = groups / 2, cap_u = 2 * groups, LA = kSweepLookahead;      // E: load / finalisation entries per record
     const size_t entry = (size_t)width * 8;
     if (n <= 0) { *why = "empty matrix"; return false; }
     // ---- list scheduling of the columns into records ---------------------------------------------------------------
@@ -178,10 +178,10 @@ static bool compile_sweep_window(const Factor &F, bool lower, i32 width, i32 gro
     // ---- geometry ------------------------------------------------------------------------------------------------
     const size_t rec_bytes = (size_t)wide_solve_record_bytes(groups);
     size_t stage = 512;
-    while (stage < rec_bytes || (size_t)(kSweepProgStages - 3) * (stage / rec_bytes) < (size_t)LA + 1) stage *= 2;
+    while (stage < rec_bytes || (size_t)(kSweepProgStages - 3) * (stage / rec_bytes) < (size_t)LA + 2) stage *= 2;   // + 1: records are read one ahead
     const size_t prog_ring = (size_t)kSweepProgStages * stage;
     W.width = width; W.groups = groups; W.nslots = nslots; W.records = nrec;
-    W.landing_entries = (LA + 1) * (lower ? cap_u : cap_u + E);          // per set: 2E update values (+ E divisors)
+    W.landing_entries = (LA + 1) * (lower ? cap_u : cap_u + E);          // per set: 2*groups update values (+ groups/2 divisors)
     W.prog.stage = (i32)stage;
     W.smem_bytes = ((size_t)nslots + (size_t)W.landing_entries) * entry + prog_ring;
     // ---- emit ----------------------------------------------------------------------------------------------------

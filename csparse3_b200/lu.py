@@ -45,6 +45,10 @@ class LuSymbolic:
         self.n, self.nnz, self.lnz, self.unz = int(sz[0]), int(sz[1]), int(sz[2]), int(sz[3])
         self.nlev_refactor, self.nlev_lsolve, self.nlev_usolve = int(sz[4]), int(sz[5]), int(sz[6])
         self.flops, self.schedule_bytes, self.max_col_len = int(sz[7]), int(sz[8]), int(sz[9])
+        # wide (lane = system) kernels: bundle width (0: not available for this pattern, the v3 kernels are used)
+        self.wide_width = int(sz[10])
+        self.wide_info = dict(width=int(sz[10]), cache_entries=int(sz[11]), landing_entries=int(sz[12]),
+                              immediate_fetches=int(sz[13]), cached_updates=int(sz[14]), smem_bytes=int(sz[15]))
         n = self.n
         self.q = np.empty(n, dtype=np.int32); self.pinv = np.empty(n, dtype=np.int32)
         self.Lp = np.empty(n + 1, dtype=np.int32); self.Li = np.empty(self.lnz, dtype=np.int32)

@@ -162,7 +162,7 @@ def run_refactor(sym, Ax):
 
 
 SWEEP_LOOKAHEAD = 3
-SWEEP_STAGES = 7
+SWEEP_STAGES = 6
 
 
 def _run_sweep(sym, which, Fx, zin):
@@ -173,8 +173,9 @@ def _run_sweep(sym, which, Fx, zin):
     EB = 8 * width
     LA, NL = SWEEP_LOOKAHEAD, SWEEP_LOOKAHEAD + 1
     SET = landing // NL
-    assert SET in (2 * E, 3 * E)
-    RB = 16 + 36 * E
+    EH = E // 2                                    # load / finalisation entries per record
+    assert SET in (2 * E, 2 * E + EH)
+    RB = 16 + 26 * E
     ring_bytes = SWEEP_STAGES * stage
     n = sym.n
     B = zin.shape[1]
@@ -192,14 +193,14 @@ def _run_sweep(sym, which, Fx, zin):
         adv = (flags >> 1) & 3
         assert p // stage == cur_stage + adv, "stage flags wrong"
         cur_stage += adv
-        loads = np.frombuffer(prog, dtype=np.int32, count=2 * E, offset=p + 16).reshape(E, 2)
-        pf = np.frombuffer(prog, dtype=np.int32, count=2 * E, offset=p + 16 + 8 * E)
-        pfd = np.frombuffer(prog, dtype=np.int32, count=E, offset=p + 16 + 16 * E)
-        fins = np.frombuffer(prog, dtype=np.int32, count=2 * E, offset=p + 16 + 20 * E).reshape(E, 2)
-        upds = np.frombuffer(prog, dtype=np.uint16, count=4 * E, offset=p + 16 + 28 * E).reshape(2 * E, 2)
+        loads = np.frombuffer(prog, dtype=np.int32, count=2 * EH, offset=p + 16).reshape(EH, 2)
+        pf = np.frombuffer(prog, dtype=np.int32, count=2 * E, offset=p + 16 + 8 * EH)
+        pfd = np.frombuffer(prog, dtype=np.int32, count=EH, offset=p + 16 + 8 * EH + 8 * E)
+        fins = np.frombuffer(prog, dtype=np.int32, count=2 * EH, offset=p + 16 + 12 * EH + 8 * E).reshape(EH, 2)
+        upds = np.frombuffer(prog, dtype=np.uint16, count=4 * E, offset=p + 16 + 20 * EH + 8 * E).reshape(2 * E, 2)
         cyc, pset = r % NL, (r + LA) % NL
         # issue: loads into slots, gathers into the landing set of record r + LA (poisoned until they land)
-        for e in range(E):
+        for e in range(EH):
             gidx, w = int(loads[e, 0]), int(loads[e, 1])
             if gidx >= 0:
                 so = (w & 0xffff)
@@ -210,9 +211,9 @@ def _run_sweep(sym, which, Fx, zin):
             if pf[u] >= 0:
                 land[pset * SET + u] = np.nan
                 pending.append((r + LA, 1, pset * SET + u, FT[pf[u]].copy()))
-        for e in range(E):
+        for e in range(EH):
             if pfd[e] >= 0:
-                assert SET == 3 * E
+                assert SET == 2 * E + EH
                 land[pset * SET + 2 * E + e] = np.nan
                 pending.append((r + LA, 1, pset * SET + 2 * E + e, FT[pfd[e]].copy()))
         keep = []
@@ -223,7 +224,7 @@ def _run_sweep(sym, which, Fx, zin):
                 keep.append((ready, kind, dst, data))
         pending = keep
         # finalisations
-        for e in range(E):
+        for e in range(EH):
             out, w = int(fins[e, 0]), int(fins[e, 1])
             if out >= 0:
                 so, div = (w & 0xffff) // EB, (w >> 16) & 0xffff
