@@ -241,6 +241,35 @@ def test_lu_grid118_bundle_widths_agree(path, S):
     assert np.array_equal(r["xw"], ox) and (r["stw"] == 0).all()          # fused path through the workspace layout
 
 
+@pytest.mark.parametrize("env", [{}, {"CSP3_WIDE_S": "16"}, {"CSP3_WIDE_S": "4"}, {"CSP3_WIDE_S": "16", "CSP3_WIDE_LANE": "4"},
+                                 {"CSP3_WIDE_F": "32"}, {"CSP3_WIDE_SOLVE": "0"}, {"CSP3_WIDE": "0"}])
+def test_lu_wide_geometries_agree(env):
+    """The wide (lane = system) kernels for several bundle widths / systems per lane, a tiny landing area (immediate
+    fetches), wide refactor + v3 solve, and v3 only: all bit-identical to the oracle on a ragged batch; one system."""
+    import os, subprocess, sys
+    g = synth.GridCase(118)
+    n, Ap, Ai, Ax0 = g.base_jacobian()
+    sym = LuSymbolic(n, Ap, Ai, Ax0)
+    Axb, bb = g.jacobian_batch(0, 37)
+    oLx, oUx, ox = _oracle_batch(sym, n, Ap, Ai, Axb, bb)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, numpy as np, torch; sys.path.insert(0, %r); from csparse3_b200 import synth; "
+            "from csparse3_b200.lu import LuSymbolic; g = synth.GridCase(118); n, Ap, Ai, Ax0 = g.base_jacobian(); "
+            "sym = LuSymbolic(n, Ap, Ai, Ax0); Axb, bb = g.jacobian_batch(0, 37); "
+            "xw, stw = sym.refactor_solve(torch.as_tensor(Axb).cuda(), torch.as_tensor(bb).cuda()); "
+            "x1, st1 = sym.refactor_solve(torch.as_tensor(Axb[:1]).cuda(), torch.as_tensor(bb[:1]).cuda()); "
+            "xh, sth = sym.refactor_solve_host(Axb, bb); "
+            "np.savez(sys.argv[1], xw=xw.cpu().numpy(), stw=stw.cpu().numpy(), x1=x1.cpu().numpy(), xh=xh, sth=sth, "
+            "wide=np.array(sym.wide_width))") % root
+    out = os.path.join(os.environ.get("TMPDIR", "/tmp"), "csp3_wide_%s.npz" % "_".join("%s%s" % kv for kv in sorted(env.items())))
+    subprocess.check_call([sys.executable, "-c", code, out], env=dict(os.environ, **env))
+    r = np.load(out)
+    assert np.array_equal(r["xw"], ox) and (r["stw"] == 0).all() and np.array_equal(r["x1"][0], ox[0])
+    assert np.array_equal(r["xh"], ox) and (r["sth"] == 0).all()
+    if env.get("CSP3_WIDE") != "0":
+        assert int(r["wide"]) == int(env.get("CSP3_WIDE_S", 8))
+
+
 def test_lu_config3_sample_device_api():
     """Config 3 pattern (2,000-bus Jacobian): device-tensor API, 24 systems vs the oracle, bit-exact."""
     import torch

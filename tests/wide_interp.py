@@ -51,7 +51,7 @@ def run_refactor(sym, Ax):
     cur_stage = 0
     an = None
     fail = np.zeros(B, dtype=np.int64)
-    stats = dict(fetches=0, immediates=0, records=0)
+    stats = dict(fetches=0, immediates=0, records=0, ops=0)
 
     def entry_of(byte_off):
         assert byte_off % EB == 0
@@ -189,7 +189,7 @@ def _run_sweep(sym, which, Fx, zin):
     nops = 0
     for r in range(nrec):
         flags, = struct.unpack_from("<H", prog, p)
-        assert p % 16 == 0 and p // ring_bytes == (p + RB - 1) // ring_bytes, "record straddles the program ring"
+        assert p % 8 == 0 and p // ring_bytes == (p + RB - 1) // ring_bytes, "record straddles the program ring"
         adv = (flags >> 1) & 3
         assert p // stage == cur_stage + adv, "stage flags wrong"
         cur_stage += adv
