@@ -122,7 +122,7 @@ constexpr int kWideProgStages = 8;      // ring slots of the program stream (see
 //                                                            (out_idx < 0: none)
 //   +..   2E  x { u16 mult_off, u16 tgt_off }                updates: slot[tgt] -= value * slot[mult]
 //                                                            (tgt_off == 0xffff: none)
-// (224 bytes for E = 8: two records per 512-byte program stage)
+// (224 bytes for E = 8: two records per 512-byte program stage).  slot_off / mult_off / tgt_off are in 16-byte units.
 // Factor values are gathered with cp.async into a landing area of kSweepLookahead + 1 record-sized sets (2E update
 // values, then E/2 divisors in the backward sweep), record r uses set r mod (kSweepLookahead + 1).  Right-hand sides
 // are copied straight into their slot at least kSweepLookahead records before the first operation that touches it.

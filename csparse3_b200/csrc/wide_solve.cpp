@@ -174,7 +174,7 @@ static bool compile_sweep_window(const Factor &F, bool lower, i32 width, i32 gro
         busy.emplace_back(last_use[i], s);
         std::push_heap(busy.begin(), busy.end(), cmp);
     }
-    if ((size_t)nslots * entry > 0xfff0) { *why = "wide sweep: too many live rows for 16-bit slot offsets"; return false; }
+    if ((size_t)nslots * entry / 16 > 0xfff0) { *why = "wide sweep: too many live rows for 16-bit slot offsets"; return false; }
     // ---- geometry ------------------------------------------------------------------------------------------------
     const size_t rec_bytes = (size_t)wide_solve_record_bytes(groups);
     size_t stage = 512;
@@ -203,18 +203,18 @@ static bool compile_sweep_window(const Factor &F, bool lower, i32 width, i32 gro
         }
         put16(b, (i64)((adv << 1) | (wrap ? 8 : 0))); put16(b, 0); put32(b, 0); put32(b, 0); put32(b, 0);
         for (i32 e = 0; e < E; ++e) {
-            if (e < (i32)R.loads.size()) { put32(b, R.loads[e].second); put16(b, (i64)((size_t)slot[R.loads[e].first] * entry)); put16(b, 0); }
+            if (e < (i32)R.loads.size()) { put32(b, R.loads[e].second); put16(b, (i64)((size_t)slot[R.loads[e].first] * entry / 16)); put16(b, 0); }
             else { put32(b, -1); put16(b, 0); put16(b, 0); }
         }
         for (i32 u = 0; u < cap_u; ++u) put32(b, (A && u < (i32)A->upds.size()) ? A->upds[u].g : -1);
         for (i32 e = 0; e < E; ++e) put32(b, (A && e < (i32)A->fins.size()) ? A->fins[e].div_g : -1);
         for (i32 e = 0; e < E; ++e) {
             if (e < (i32)R.fins.size()) {
-                put32(b, R.fins[e].out); put16(b, (i64)((size_t)slot[R.fins[e].row] * entry)); put16(b, R.fins[e].div_g >= 0 ? 1 : 0);
+                put32(b, R.fins[e].out); put16(b, (i64)((size_t)slot[R.fins[e].row] * entry / 16)); put16(b, R.fins[e].div_g >= 0 ? 1 : 0);
             } else { put32(b, -1); put16(b, 0); put16(b, 0); }
         }
         for (i32 u = 0; u < cap_u; ++u) {
-            if (u < (i32)R.upds.size()) { put16(b, (i64)((size_t)slot[R.upds[u].mult_row] * entry)); put16(b, (i64)((size_t)slot[R.upds[u].tgt_row] * entry)); }
+            if (u < (i32)R.upds.size()) { put16(b, (i64)((size_t)slot[R.upds[u].mult_row] * entry / 16)); put16(b, (i64)((size_t)slot[R.upds[u].tgt_row] * entry / 16)); }
             else { put16(b, 0); put16(b, 0xffff); }
         }
         if (b.size() != rec_bytes) { *why = "wide sweep: internal error (record size)"; return false; }

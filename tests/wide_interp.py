@@ -203,7 +203,7 @@ def _run_sweep(sym, which, Fx, zin):
         for e in range(EH):
             gidx, w = int(loads[e, 0]), int(loads[e, 1])
             if gidx >= 0:
-                so = (w & 0xffff)
+                so = (w & 0xffff) * 16
                 assert so % EB == 0 and so // EB < nslots
                 slots[so // EB] = np.nan
                 pending.append((r + LA, 0, so // EB, zin[gidx].copy()))
@@ -227,7 +227,7 @@ def _run_sweep(sym, which, Fx, zin):
         for e in range(EH):
             out, w = int(fins[e, 0]), int(fins[e, 1])
             if out >= 0:
-                so, div = (w & 0xffff) // EB, (w >> 16) & 0xffff
+                so, div = (w & 0xffff) * 16 // EB, (w >> 16) & 0xffff
                 v = slots[so].copy()
                 assert not np.isnan(v).any(), "finalisation of a row that has not landed (record %d)" % r
                 if div:
@@ -240,8 +240,8 @@ def _run_sweep(sym, which, Fx, zin):
         ok = upds[:, 1] != 0xffff
         if ok.any():
             idx = np.nonzero(ok)[0]
-            mul = upds[idx, 0].astype(np.int64) // EB
-            tgt = upds[idx, 1].astype(np.int64) // EB
+            mul = upds[idx, 0].astype(np.int64) * 16 // EB
+            tgt = upds[idx, 1].astype(np.int64) * 16 // EB
             assert len(set(tgt.tolist())) == len(tgt) and not (set(tgt.tolist()) & set(mul.tolist()))
             lv = land[cyc * SET + idx]
             assert not np.isnan(lv).any() and not np.isnan(slots[mul]).any() and not np.isnan(slots[tgt]).any(), \
