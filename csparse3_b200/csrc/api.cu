@@ -573,6 +573,7 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
         D.wide_ok = true; D.wide_S = W.width; D.wide_R = W.width * W.groups / 32;
         D.wrf_prog = (const uint8_t *)at(i_wrf); D.wrf_prog_bytes = (i32)W.prog.bytes.size(); D.wrf_prog_stage = W.prog.stage;
         D.wrf_acc_slots = W.acc_slots; D.wrf_lsrc_entries = W.ring_entries + W.stage_entries; D.wrf_smem = W.smem_bytes;
+        D.wrf_groups = W.ngroups;
         if (wsolve) {
             D.wide_solve_ok = true;
             D.wfs_prog = (const uint8_t *)at(i_wfs); D.wfs_prog_bytes = (i32)sym->WF.prog.bytes.size(); D.wfs_prog_stage = sym->WF.prog.stage;

@@ -35,7 +35,7 @@ struct DevSchedule {
     i32 ls_nslots = 0, us_nslots = 0, ur_nslots = 0, ur_max_len = 0;
     // wide (lane = system) refactor program, lu_wide.cu
     bool wide_ok = false;
-    i32 wide_S = 0, wide_R = 2, wrf_prog_bytes = 0, wrf_prog_stage = 0, wrf_acc_slots = 0, wrf_lsrc_entries = 0;
+    i32 wide_S = 0, wide_R = 2, wrf_groups = 0, wrf_prog_bytes = 0, wrf_prog_stage = 0, wrf_acc_slots = 0, wrf_lsrc_entries = 0;
     const uint8_t *wrf_prog = nullptr;
     size_t wrf_smem = 0;
     // wide triangular sweeps (forward / backward)

@@ -73,20 +73,32 @@ constexpr int kSvHeader = 24;
 // BYTE offsets from the start of the value area (acc first, lsrc right behind it), all global positions of the
 // fetches are 16-byte units, so decoding is adds only.  EB = 8*S is the size of one bundle entry.
 //
-// Column record (48-byte header).  The first record of a program is a preamble (ucnt == 0) that only loads the
-// A values of column 0.
-//   +0   i32 up           first entry of U(:,k) in the bundle's U array
-//   +4   i32 lp           Lp[k] (the unit diagonal slot)
-//   +8   u16 ucnt         +10 u16 lcnt
-//   +12  u16 a_cnt        +14 u16 pair_cnt       (pairs with an empty source column are not emitted)
-//   +16  u16 ring         lsrc entry that receives L(1:,k); 0xffff: not cached
-//   +18  u16 an_cnt       A entries of the NEXT column that are loaded into registers while this column is
-//                         eliminated: min(a_cnt of k+1, kWideARegs * E), E = lane groups of the kernel
+// Group record (48-byte header).  A group is a set of up to kWideGroupCols mutually independent columns (none is
+// a source of another, all their sources were finalised by earlier groups) that are eliminated together: their
+// accumulators occupy consecutive slot ranges, their updates share chunk records, one pass finalises them.  The
+// elimination order inside the program is a list schedule of the columns (any order in which sources come first
+// gives the same bits: a column's own arithmetic is untouched); long columns form groups of one.  The first record
+// of a program is a preamble (ncols == 0) that only loads the A values of the first group.
+//   +0   8 bytes reserved
+//   +8   u16 ncols        +10 u16 nslots         accumulator slots of the group (cleared by the finalisation)
+//   +12  u16 a_cnt        +14 u16 chunk_cnt
+//   +16  u16 fin_cnt      finalisation records that follow the chunk records
+//   +18  u16 an_cnt       A entries of the NEXT group that are loaded into registers while this group is
+//                         eliminated: min(a_cnt of the next group, kWideARegs * E), E = lane groups of the kernel
 //   +20  u16 fetch_dst16  +22 u16 fetch_units (16-byte units, 0: none)      +24 i32 fetch_src16
-//   +28  i32 pf_src       first A entry of the column kWidePfCols columns ahead (L2 prefetch), -1: none
-//   +32  u16 pf_cnt       +34 u8 flags (bits 1-2: stages entered, bit 3: wrap)      +35..47 reserved
-//   +48  a_cnt x u16 accumulator byte offset; pad to 4; an_cnt x i32 index into the system's Ax (next column);
-//        then the indices of this column's own entries beyond the register-held ones; pad to 16
+//   +28  u16 npf          A runs to pull into L2 (those of the group kWidePfGroups ahead)
+//   +30  u16 reserved     +32 u16 reserved      +34 u8 flags (bits 1-2: stages entered, bit 3: wrap)
+//   +48  kWideGroupCols x { i32 col1 (column + 1, 0: none), u16 pivot_off, u16 0 }
+//   +..  kWideGroupCols x { i32 pf_src (first A entry of a run, -1: none), i32 pf_cnt }
+//   +..  a_cnt x u16 accumulator byte offset; pad to 4; an_cnt x i32 index into the system's Ax (next group);
+//        then the indices of this group's own entries beyond the register-held ones; pad to 16
+// Finalisation record (16-byte header + C entries of 8 bytes, C = 2 * lane groups; same size as a chunk record):
+//   +0   i32 fetch_src16  +4 u16 fetch_dst16     +6 u16 fetch_units (0: none)      (a look-ahead fetch, as in chunks)
+//   +8   u16 flags (bits 1-2 stages entered, bit 3 wrap)
+//   +16  C x { i32 gout, u16 slot_off, u16 cache_off }
+//        gout: bit 31 = L entry (value = slot / pivot of its column), bits 28-30 = index of the column inside the
+//        group, bits 0-27 = position in the bundle's L or U array; slot_off == 0xffff: no entry;
+//        cache_off != 0xffff: the L entry is also kept in the L cache (byte offset in the value area)
 // Chunk record (16-byte header + C entries of 8 bytes, C = 2 * lane groups): up to C update operations
 //   acc[tgt] -= lsrc[src] * acc[mult]
 // that are mutually independent (no two share a target, no multiplier is a target of the chunk), taken in order
@@ -97,12 +109,14 @@ constexpr int kSvHeader = 24;
 //   +8   u16 flags: bit 0 = the fetch of THIS record must land before it is used (immediate),
 //                   bits 1-2 = stages entered, bit 3 = wrap                   +10..15 reserved
 //   +16  C x { u16 src_off, u16 mult_off, u16 tgt_off, u16 valid }   (byte offsets in the value area)
-// The column record's pair_cnt field counts the chunk records that follow it.
+
 namespace csp3 {
 constexpr int kWideLookahead = 4;     // records between a fetch and its use == pending cp.async groups allowed
 constexpr int kWideARegs = 2;         // A values (per system) a lane holds in registers one column ahead
-constexpr int kWidePfCols = 8;        // L2 prefetch distance of the A values, in columns
-constexpr int kWideColHeader = 48;
+constexpr int kWidePfGroups = 4;      // L2 prefetch distance of the A values, in groups
+constexpr int kWideGroupCols = 8;     // columns per group (one lane group each in the reciprocal pass)
+constexpr int kWideGroupA = 32;       // A entries per group of more than one column
+constexpr int kWideColHeader = 48;     // group record header
 constexpr int kWideChunkHeader = 16;
 constexpr int kWideProgStages = 8;      // ring slots of the program stream (see WideStream in lu_wide.cu)
 }  // namespace csp3

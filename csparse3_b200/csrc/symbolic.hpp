@@ -115,7 +115,7 @@ struct WideProgram {
     i32 acc_slots = 0, ring_entries = 0, stage_entries = 0;
     size_t smem_bytes = 0;
     Program prog;
-    i32 records = 0, immediate_fetches = 0;
+    i32 records = 0, immediate_fetches = 0, ngroups = 0;
     i64 near_fma = 0, far_fma = 0;         // update operations whose source column is cached / fetched
     i64 chunks = 0, chunk_ops = 0;         // chunk records and the update operations they hold
 };

@@ -1,8 +1,10 @@
 // wide_program.cpp -- host compiler of the "wide" (lane = system) refactor program executed by lu_wide.cu.
 // Record formats: program.hpp.  No reference counterpart; the arithmetic the program
 // encodes is the frozen-pattern left-looking cs_lu column update of oracle/csp3_oracle.c, operation for
-// operation and in the same order.
+// operation and, for every column, in the same order.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "program.hpp"
@@ -22,16 +24,24 @@ struct Bytes {
 
 struct Fetch { i32 len = 0, dst = 0, src = 0; };
 
-struct Op { i32 pair, t; };      // update t of pair `pair` (index into Schedule::pairs)
+struct Op { i32 pair, t, base; };   // update t of pair `pair` (index into Schedule::pairs); slot base of its column
+
+struct FinEnt { i32 gout, slot, cache; };       // cache: lsrc entry or -1
 
 struct Rec {
-    bool is_col = false;
-    i32 k = -1;                 // column (-1: preamble)
+    int kind = 0;               // 0 group header, 1 chunk, 2 finalisation
+    i32 group = -1;             // group index (-1: preamble)
     std::vector<Op> ops;        // chunk records
+    std::vector<FinEnt> fins;   // finalisation records
     i32 new_far = -1;           // pair whose landing run is first used by this chunk (-1: none)
     bool immediate = false;
     Fetch fetch;
-    i32 ring = 0xffff;          // column records
+};
+
+struct Group {
+    std::vector<i32> cols, base;
+    i32 nslots = 0, a_cnt = 0;
+    i32 first_rec = 0, chunk_cnt = 0, fin_cnt = 0;
 };
 
 inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -43,286 +53,406 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
 {
     W = WideProgram();
     const i32 n = (i32)S.cols.size();
-    const std::vector<i32> &Lp = F.Lp;
+    const std::vector<i32> &Lp = F.Lp, &Up = F.Up, &Ui = F.Ui;
     if (width != 4 && width != 8 && width != 16 && width != 32) { *why = "wide bundle width must be 4, 8, 16 or 32"; return false; }
     if (n == 0) { *why = "empty matrix"; return false; }
-    const i32 cap = 2 * groups;                                  // update operations per chunk
+    if (F.Li.size() >= (1u << 28) || F.Ui.size() >= (1u << 28)) { *why = "wide refactor: factor too large"; return false; }
+    const i32 cap = 2 * groups;                                  // operations per chunk / finalisation record
+    const i32 cover = kWideARegs * groups;                       // A values the kernel keeps in registers
     i32 max_llen = 1, max_acnt = 0;
     for (const PairDesc &pd : S.pairs) max_llen = std::max(max_llen, pd.llen);
     for (const ColDesc &cd : S.cols) max_acnt = std::max(max_acnt, cd.a_cnt);
+    const i32 group_a = std::max<i32>(kWideGroupA, max_acnt);
     // ---- record sizes -> program stage size ----------------------------------------------------------------
     const size_t chunk_rec = (size_t)kWideChunkHeader + 8 * (size_t)cap;
-    const size_t max_col_rec = round_up(round_up((size_t)kWideColHeader + 2 * (size_t)max_acnt, 4) + 4 * (size_t)max_acnt, 16);
-    const size_t max_rec = std::max(chunk_rec, max_col_rec);
-    // The reader requests stage cur + kWideProgStages - 2 when it enters stage cur and relies on stage cur + 1
-    // having landed: that load was requested kWideProgStages - 3 stages earlier and must be at least
-    // kWideLookahead + 3 records old (its group is only waited for kWideLookahead records later, and the kernel
-    // reads records up to two ahead).
+    const size_t max_grp_rec = round_up(round_up((size_t)kWideColHeader + 16 * (size_t)kWideGroupCols + 2 * (size_t)group_a, 4) +
+                                        4 * (size_t)group_a, 16);
+    const size_t max_rec = std::max(chunk_rec, max_grp_rec);
     size_t stage = 512;
-    while (stage < max_rec || (size_t)(kWideProgStages - 3) * (stage / max_rec) < (size_t)kWideLookahead + 3) stage *= 2;
-    const size_t prog_ring = (size_t)kWideProgStages * stage;
+    while (stage < max_rec) stage *= 2;
     // ---- shared-memory geometry ---------------------------------------------------------------------------
+    // value area: acc_slots accumulator slots | 2 * kWideGroupCols pivot / reciprocal entries | L cache | landing area
     const size_t entry = (size_t)width * 8;
     const i32 acc_slots = (S.max_col_len + 1 + 1) & ~1;
+    const i32 table = 2 * kWideGroupCols;
     i32 stage_entries = stage_override > 0 ? stage_override : (i32)round_up((size_t)(kWideLookahead + 1) * max_llen, 8);
     stage_entries = std::max(stage_entries, (i32)round_up((size_t)max_llen, 8));
-    const size_t fixed = (size_t)acc_slots * entry + prog_ring + (size_t)stage_entries * entry;
-    if (fixed + 8 * entry > smem_budget) { *why = "wide refactor working set exceeds the shared-memory budget"; return false; }
-    i32 ring_entries = (i32)((smem_budget - fixed) / entry);
-    if (ring_override > 0) ring_entries = std::min(ring_entries, ring_override);
-    if ((size_t)(acc_slots + ring_entries + stage_entries) * entry > 0xfff0) {
-        // all value offsets are 16-bit byte offsets
-        const size_t room = (0xfff0 / entry);
-        if (room <= (size_t)acc_slots + (size_t)stage_entries + 8) { *why = "wide refactor: value area too large for 16-bit offsets"; return false; }
-        ring_entries = (i32)(room - (size_t)acc_slots - (size_t)stage_entries);
-    }
-    W.width = width; W.groups = groups; W.acc_slots = acc_slots; W.ring_entries = ring_entries; W.stage_entries = stage_entries;
-    W.prog.stage = (i32)stage;
-    W.smem_bytes = (size_t)acc_slots * entry + (size_t)(ring_entries + stage_entries) * entry + prog_ring;
 
-    // ---- pass A: L cache (ring) simulation, column by column -> near / far for every pair; chunk packing -------
-    // Column k's strict L part is placed in the ring when the column is finalised (after its last record), so every
-    // pair of column k sees the ring as the columns before k left it.
-    std::vector<i32> ring_pos((size_t)n, -1), owner((size_t)std::max(ring_entries, 1), -1);
-    std::vector<i32> pair_src((size_t)S.pairs.size(), -1);       // lsrc entry of the pair's source column (near pairs)
-    std::vector<i32> pair_col((size_t)S.pairs.size(), -1);       // source column j
-    std::vector<char> pair_far((size_t)S.pairs.size(), 0);
-    i32 cur = 0;
-    auto ring_valid = [&](i32 j) {
-        const i32 pos = ring_pos[j], len = Lp[j + 1] - Lp[j] - 1;
-        if (pos < 0) return false;
-        for (i32 t = 0; t < len; ++t) if (owner[pos + t] != j) return false;
+    // ---- phase 0: list schedule of the columns into groups -------------------------------------------------------
+    // sources of column k: the off-diagonal rows of U(:,k)
+    std::vector<char> done((size_t)n, 0), in_group((size_t)n, 0);
+    std::vector<Group> G;
+    {
+        i32 lo = 0;                                              // oldest unfinished column
+        const i32 window = 96;
+        while (lo < n) {
+            Group g;
+            i32 a_total = 0;
+            for (i32 k = lo; k < std::min(n, lo + window) && (i32)g.cols.size() < kWideGroupCols; ++k) {
+                if (done[k]) continue;
+                const ColDesc &cd = S.cols[k];
+                const i32 len = cd.ucnt + cd.lcnt - 1;
+                bool ready = true;
+                for (i32 p = Up[k]; p < Up[k + 1] - 1 && ready; ++p) ready = done[Ui[p]] && !in_group[Ui[p]];
+                if (!ready) continue;
+                if (!g.cols.empty() && (g.nslots + len > acc_slots || a_total + cd.a_cnt > kWideGroupA)) continue;
+                g.cols.push_back(k); g.base.push_back(g.nslots);
+                g.nslots += len; a_total += cd.a_cnt;
+                in_group[k] = 1;
+                if (len > acc_slots / 2) break;                  // a long column runs alone
+            }
+            if (g.cols.empty()) { *why = "wide refactor: internal error (no ready column)"; return false; }
+            for (i32 k : g.cols) { done[k] = 1; in_group[k] = 0; }
+            g.a_cnt = a_total;
+            G.push_back(std::move(g));
+            while (lo < n && done[lo]) ++lo;
+        }
+    }
+    const i32 ngroups = (i32)G.size();
+
+    auto geometry = [&](size_t stg, i32 &ring_entries) -> bool {
+        const size_t prog_ring = (size_t)kWideProgStages * stg;
+        const size_t fixed = ((size_t)acc_slots + table) * entry + prog_ring + (size_t)stage_entries * entry;
+        if (fixed + 8 * entry > smem_budget) return false;
+        ring_entries = (i32)((smem_budget - fixed) / entry);
+        if (ring_override > 0) ring_entries = std::min(ring_entries, ring_override);
+        if (((size_t)acc_slots + table + ring_entries + stage_entries) * entry > 0xfff0) {
+            const size_t room = (0xfff0 / entry);
+            if (room <= (size_t)acc_slots + table + (size_t)stage_entries + 8) return false;
+            ring_entries = (i32)(room - (size_t)acc_slots - table - (size_t)stage_entries);
+        }
         return true;
     };
-    std::vector<Rec> recs;
-    recs.reserve(S.pairs.size() + (size_t)n + 1);
-    std::vector<i32> col_rec((size_t)n + 1, 0);          // index of the column record of k (n: one past the end)
-    { Rec r; r.is_col = true; r.k = -1; recs.push_back(r); }
-    std::vector<i32> stamp_t(65536, -1);                 // accumulator slot -> chunk id that writes it
-    i32 chunk_id = 0;
-    for (i32 k = 0; k < n; ++k) {
-        col_rec[k] = (i32)recs.size();
-        { Rec r; r.is_col = true; r.k = k; recs.push_back(r); }
-        const ColDesc &cd = S.cols[k];
-        Rec ch;
-        ch.k = k;
-        bool open = false;
-        auto flush = [&]() { if (open) { recs.push_back(ch); ch = Rec(); ch.k = k; open = false; ++chunk_id; } };
-        for (i32 pi = cd.pair_ptr; pi < cd.pair_ptr + cd.pair_cnt; ++pi) {
-            const PairDesc &pd = S.pairs[pi];
-            if (pd.llen == 0) continue;
-            const i32 j = (i32)(std::upper_bound(Lp.begin(), Lp.end(), pd.lstart - 1) - Lp.begin()) - 1;
-            pair_col[pi] = j;
-            if (ring_valid(j)) { pair_src[pi] = ring_pos[j]; W.near_fma += pd.llen; }
-            else { pair_far[pi] = 1; W.far_fma += pd.llen; }
-            bool first_of_pair = true;
-            for (i32 t = 0; t < pd.llen; ++t) {
-                const i32 tgt = S.upd_map[(size_t)pd.mapstart + t];
-                bool fits = open && (i32)ch.ops.size() < cap && stamp_t[tgt] != chunk_id && stamp_t[pd.moff] != chunk_id;
-                // at most one pair per chunk may bring in a new landing run (one fetch slot per record)
-                if (fits && first_of_pair && pair_far[pi] && ch.new_far >= 0) fits = false;
-                if (!fits) { flush(); open = true; }
-                if (first_of_pair && pair_far[pi]) ch.new_far = pi;
-                first_of_pair = false;
-                ch.ops.push_back({pi, t});
-                stamp_t[tgt] = chunk_id;
+
+    for (int attempt = 0; attempt < 4; ++attempt, stage *= 2) {
+        W = WideProgram();
+        i32 ring_entries = 0;
+        if (!geometry(stage, ring_entries)) { *why = "wide refactor working set exceeds the shared-memory budget"; return false; }
+        const size_t prog_ring = (size_t)kWideProgStages * stage;
+        const size_t lsrc0 = (size_t)acc_slots + table;          // first lsrc entry, in entries of the value area
+        W.width = width; W.groups = groups; W.acc_slots = acc_slots; W.ring_entries = ring_entries; W.stage_entries = stage_entries;
+        W.prog.stage = (i32)stage;
+        W.smem_bytes = (lsrc0 + (size_t)ring_entries + stage_entries) * entry + prog_ring;
+
+        // ---- phase 1: L cache (ring) simulation group by group; chunk packing; finalisation records -----------------
+        std::vector<i32> ring_pos((size_t)n, -1), owner((size_t)std::max(ring_entries, 1), -1);
+        std::vector<i32> pair_src((size_t)S.pairs.size(), -1), pair_col((size_t)S.pairs.size(), -1);
+        std::vector<char> pair_far((size_t)S.pairs.size(), 0);
+        i32 cur = 0;
+        auto ring_valid = [&](i32 j) {
+            const i32 pos = ring_pos[j], len = Lp[j + 1] - Lp[j] - 1;
+            if (pos < 0) return false;
+            for (i32 t = 0; t < len; ++t) if (owner[pos + t] != j) return false;
+            return true;
+        };
+        std::vector<Rec> recs;
+        recs.reserve(S.pairs.size() + 2 * (size_t)n + 1);
+        { Rec r; r.kind = 0; r.group = -1; recs.push_back(r); }
+        std::vector<i32> stamp_t((size_t)acc_slots + 1, -1);     // accumulator slot -> chunk id that writes it
+        i32 chunk_id = 0;
+        for (i32 gi = 0; gi < ngroups; ++gi) {
+            Group &g = G[gi];
+            g.first_rec = (i32)recs.size();
+            { Rec r; r.kind = 0; r.group = gi; recs.push_back(r); }
+            // per column: cursor over its pairs / entries
+            struct Cur { i32 pi, pend, t; bool first_of_pair; };
+            std::vector<Cur> cs;
+            for (size_t c = 0; c < g.cols.size(); ++c) {
+                const ColDesc &cd = S.cols[g.cols[c]];
+                cs.push_back({cd.pair_ptr, cd.pair_ptr + cd.pair_cnt, 0, true});
+                for (i32 pi = cd.pair_ptr; pi < cd.pair_ptr + cd.pair_cnt; ++pi) {
+                    const PairDesc &pd = S.pairs[pi];
+                    if (pd.llen == 0) continue;
+                    const i32 j = (i32)(std::upper_bound(Lp.begin(), Lp.end(), pd.lstart - 1) - Lp.begin()) - 1;
+                    pair_col[pi] = j;
+                    if (ring_valid(j)) { pair_src[pi] = ring_pos[j]; W.near_fma += pd.llen; }
+                    else { pair_far[pi] = 1; W.far_fma += pd.llen; }
+                }
+            }
+            // chunks: round robin over the columns, every column strictly in its own order
+            size_t remaining = g.cols.size();
+            std::vector<char> fin_col(g.cols.size(), 0);
+            while (remaining > 0) {
+                Rec ch; ch.kind = 1; ch.group = gi;
+                bool any = false;
+                for (size_t c = 0; c < g.cols.size(); ++c) {
+                    Cur &u = cs[c];
+                    while (!fin_col[c]) {
+                        while (u.pi < u.pend && (S.pairs[u.pi].llen == 0 || u.t >= S.pairs[u.pi].llen)) { ++u.pi; u.t = 0; u.first_of_pair = true; }
+                        if (u.pi >= u.pend) { fin_col[c] = 1; --remaining; break; }
+                        const PairDesc &pd = S.pairs[u.pi];
+                        const i32 tgt = g.base[c] + S.upd_map[(size_t)pd.mapstart + u.t], mult = g.base[c] + pd.moff;
+                        if ((i32)ch.ops.size() >= cap || stamp_t[tgt] == chunk_id || stamp_t[mult] == chunk_id) break;
+                        // at most one pair per chunk may bring in a new landing run (one fetch slot per record)
+                        if (u.first_of_pair && pair_far[u.pi] && ch.new_far >= 0) break;
+                        if (u.first_of_pair && pair_far[u.pi]) ch.new_far = u.pi;
+                        u.first_of_pair = false;
+                        ch.ops.push_back({u.pi, u.t, g.base[c]});
+                        stamp_t[tgt] = chunk_id;
+                        ++u.t;
+                        any = true;
+                    }
+                }
+                if (any) { recs.push_back(ch); ++chunk_id; ++g.chunk_cnt; }
+            }
+            // finalisation: cache the strict L part of every column, emit fixed-size finalisation records
+            std::vector<FinEnt> fe;
+            for (size_t c = 0; c < g.cols.size(); ++c) {
+                const i32 k = g.cols[c];
+                const ColDesc &cd = S.cols[k];
+                const i32 len = Lp[k + 1] - Lp[k] - 1;
+                i32 pos = -1;
+                if (len > 0 && len <= ring_entries) {
+                    if (cur + len > ring_entries) cur = 0;
+                    pos = cur;
+                    for (i32 t = 0; t < len; ++t) owner[pos + t] = k;
+                    cur += len;
+                    ring_pos[k] = pos;
+                }
+                for (i32 t = 0; t < cd.ucnt; ++t) fe.push_back({cd.up + t, g.base[c] + t, -1});
+                for (i32 t = 0; t < cd.lcnt - 1; ++t)
+                    fe.push_back({(i32)(0x80000000u | ((uint32_t)c << 28) | (uint32_t)(cd.lp + 1 + t)), g.base[c] + cd.ucnt + t, pos >= 0 ? pos + t : -1});
+            }
+            for (size_t o = 0; o < fe.size(); o += (size_t)cap) {
+                Rec fr; fr.kind = 2; fr.group = gi;
+                fr.fins.assign(fe.begin() + (long)o, fe.begin() + (long)std::min(fe.size(), o + (size_t)cap));
+                recs.push_back(fr);
+                ++g.fin_cnt;
             }
         }
-        flush();
-        // finalisation of column k: cache its strict L part
-        const i32 len = Lp[k + 1] - Lp[k] - 1;
-        i32 pos = 0xffff;
-        if (len > 0 && len <= ring_entries) {
-            if (cur + len > ring_entries) cur = 0;
-            pos = cur;
-            for (i32 t = 0; t < len; ++t) owner[pos + t] = k;
-            cur += len;
-            ring_pos[k] = pos;
-        }
-        recs[col_rec[k]].ring = pos;
-    }
-    col_rec[n] = (i32)recs.size();
-    const i32 nrec = (i32)recs.size();
-    // last record that reads each far pair's landing run
-    std::vector<i32> last_use((size_t)S.pairs.size(), -1);
-    for (i32 r = 0; r < nrec; ++r)
-        for (const Op &o : recs[r].ops) if (pair_far[o.pair]) last_use[o.pair] = r;
+        const i32 nrec = (i32)recs.size();
+        // record after which column j's L entries are in global memory: the last finalisation record of its group
+        std::vector<i32> final_rec((size_t)n, 0);
+        for (i32 gi = 0; gi < ngroups; ++gi)
+            for (i32 k : G[gi].cols) final_rec[k] = G[gi].first_rec + G[gi].chunk_cnt + G[gi].fin_cnt;      // first record AFTER the group
+        std::vector<i32> last_use((size_t)S.pairs.size(), -1);
+        for (i32 r = 0; r < nrec; ++r)
+            for (const Op &o : recs[r].ops) if (pair_far[o.pair]) last_use[o.pair] = r;
 
-    // ---- pass B: landing-area allocation in issue order ------------------------------------------------------
-    struct Run { i32 pair, start, len; };
-    std::vector<Run> live;
-    i32 scur = 0;
-    auto overlaps = [&](i32 s, i32 len) {
-        for (const Run &u : live) if (s < u.start + u.len && u.start < s + len) return true;
-        return false;
-    };
-    auto alloc = [&](i32 len, i32 pair) -> i32 {
-        // first fit from the cursor, wrapping once; a run is never split by the wrap
-        const i32 positions = stage_entries - len + 1;
-        if (positions <= 0) return -1;
-        const i32 first = scur < positions ? scur : 0;
-        for (i32 probe = 0; probe < positions; ++probe) {
-            const i32 s = (first + probe) % positions;
-            if (!overlaps(s, len)) { live.push_back({pair, s, len}); scur = s + len; return s; }
-        }
-        return -1;
-    };
-    auto drop = [&](i32 pair) {
-        for (size_t u = 0; u < live.size(); ++u) if (live[u].pair == pair) { live.erase(live.begin() + (long)u); return; }
-    };
-    std::vector<char> served((size_t)S.pairs.size(), 0);
-    for (i32 x = 0; x < nrec; ++x) {
-        // (1) look-ahead fetch for the chunk kWideLookahead records from now
-        const i32 r = x + kWideLookahead;
-        if (r < nrec && recs[r].new_far >= 0) {
-            const i32 pi = recs[r].new_far, j = pair_col[pi];
-            const PairDesc &pd = S.pairs[pi];
-            const bool final_by_now = col_rec[j + 1] <= x;      // column j was finalised before record x starts
-            const i32 s = final_by_now ? alloc(pd.llen, pi) : -1;
-            if (s >= 0) {
+        // ---- phase 2: landing-area allocation in issue order ---------------------------------------------------------
+        struct Run { i32 pair, start, len; };
+        std::vector<Run> live;
+        i32 scur = 0;
+        auto overlaps = [&](i32 s, i32 len) {
+            for (const Run &u : live) if (s < u.start + u.len && u.start < s + len) return true;
+            return false;
+        };
+        auto alloc = [&](i32 len, i32 pair) -> i32 {
+            const i32 positions = stage_entries - len + 1;
+            if (positions <= 0) return -1;
+            const i32 first = scur < positions ? scur : 0;
+            for (i32 probe = 0; probe < positions; ++probe) {
+                const i32 s = (first + probe) % positions;
+                if (!overlaps(s, len)) { live.push_back({pair, s, len}); scur = s + len; return s; }
+            }
+            return -1;
+        };
+        auto drop = [&](i32 pair) {
+            for (size_t u = 0; u < live.size(); ++u) if (live[u].pair == pair) { live.erase(live.begin() + (long)u); return; }
+        };
+        std::vector<char> served((size_t)S.pairs.size(), 0);
+        bool failed = false;
+        for (i32 x = 0; x < nrec && !failed; ++x) {
+            const i32 r = x + kWideLookahead;
+            if (r < nrec && recs[r].new_far >= 0) {
+                const i32 pi = recs[r].new_far, j = pair_col[pi];
+                const PairDesc &pd = S.pairs[pi];
+                const bool final_by_now = final_rec[j] <= x;         // column j was finalised before record x starts
+                const i32 s = final_by_now ? alloc(pd.llen, pi) : -1;
+                if (s >= 0) {
+                    recs[x].fetch.len = pd.llen; recs[x].fetch.dst = ring_entries + s; recs[x].fetch.src = pd.lstart;
+                    pair_src[pi] = ring_entries + s;
+                    served[pi] = 1;
+                }
+            }
+            if (recs[x].new_far >= 0 && !served[recs[x].new_far]) {
+                const i32 pi = recs[x].new_far;
+                const PairDesc &pd = S.pairs[pi];
+                if (recs[x].fetch.len != 0) {
+                    const i32 p2 = recs[x + kWideLookahead].new_far;
+                    drop(p2);
+                    recs[x].fetch = Fetch();
+                    served[p2] = 0;
+                }
+                i32 s = alloc(pd.llen, pi);
+                while (s < 0) {
+                    i32 victim = -1, vrec = -1;
+                    for (i32 y = x + 1; y < std::min(nrec, x + kWideLookahead + 1); ++y)
+                        if (recs[y].new_far >= 0 && served[recs[y].new_far]) { victim = recs[y].new_far; vrec = y; }
+                    if (victim < 0) { failed = true; break; }
+                    recs[vrec - kWideLookahead].fetch = Fetch();
+                    served[victim] = 0;
+                    drop(victim);
+                    s = alloc(pd.llen, pi);
+                }
+                if (failed) break;
                 recs[x].fetch.len = pd.llen; recs[x].fetch.dst = ring_entries + s; recs[x].fetch.src = pd.lstart;
                 pair_src[pi] = ring_entries + s;
                 served[pi] = 1;
+                recs[x].immediate = true;
+                ++W.immediate_fetches;
+            }
+            for (size_t u = 0; u < live.size();) {
+                if (last_use[live[u].pair] == x) live.erase(live.begin() + (long)u); else ++u;
             }
         }
-        // (2) chunks whose new run could not be requested ahead of time fetch for themselves and wait
-        if (recs[x].new_far >= 0 && !served[recs[x].new_far]) {
-            const i32 pi = recs[x].new_far;
-            const PairDesc &pd = S.pairs[pi];
-            if (recs[x].fetch.len != 0) {
-                // this record already carries a look-ahead fetch for a later chunk: that one becomes immediate
-                const i32 p2 = recs[x + kWideLookahead].new_far;
-                drop(p2);
-                recs[x].fetch = Fetch();
-                served[p2] = 0;
-            }
-            i32 s = alloc(pd.llen, pi);
-            while (s < 0) {
-                // make room: cancel the youngest look-ahead fetch (its chunk will fetch for itself later)
-                i32 victim = -1, vrec = -1;
-                for (i32 y = x + 1; y < std::min(nrec, x + kWideLookahead + 1); ++y)
-                    if (recs[y].new_far >= 0 && served[recs[y].new_far]) { victim = recs[y].new_far; vrec = y; }
-                if (victim < 0) { *why = "wide refactor: landing area too small"; return false; }
-                recs[vrec - kWideLookahead].fetch = Fetch();
-                served[victim] = 0;
-                drop(victim);
-                s = alloc(pd.llen, pi);
-            }
-            recs[x].fetch.len = pd.llen; recs[x].fetch.dst = ring_entries + s; recs[x].fetch.src = pd.lstart;
-            pair_src[pi] = ring_entries + s;
-            served[pi] = 1;
-            recs[x].immediate = true;
-            ++W.immediate_fetches;
-        }
-        // (3) runs whose last reader is record x are free again
-        for (size_t u = 0; u < live.size();) {
-            if (last_use[live[u].pair] == x) live.erase(live.begin() + (long)u); else ++u;
-        }
-    }
+        if (failed) { *why = "wide refactor: landing area too small"; return false; }
 
-    // ---- emit ----------------------------------------------------------------------------------------------------
-    std::vector<uint8_t> &out = W.prog.bytes;
-    std::vector<std::vector<uint8_t>> blobs((size_t)nrec);
-    for (i32 r = 0; r < nrec; ++r) {
-        const Rec &R = recs[r];
-        std::vector<uint8_t> &b = blobs[r];
-        Bytes B(b);
-        const i64 fdst16 = (i64)(((size_t)acc_slots + R.fetch.dst) * entry / 16), funits = (i64)((size_t)R.fetch.len * entry / 16);
-        const i32 fsrc16 = (i32)((size_t)R.fetch.src * entry / 16);
-        if (R.is_col) {
-            const i32 k = R.k;
-            const bool pre = k < 0;
-            const ColDesc *cd = pre ? nullptr : &S.cols[k];
-            const ColDesc *nx = (k + 1 < n) ? &S.cols[k + 1] : nullptr;
-            const ColDesc *pf = (k + kWidePfCols < n && k + kWidePfCols >= 0) ? &S.cols[k + kWidePfCols] : nullptr;
-            const i32 chunk_cnt = pre ? 0 : (k + 1 < n ? col_rec[k + 1] : nrec) - col_rec[k] - 1;
-            if (chunk_cnt > 0xffff) { *why = "wide refactor: too many chunks in a column"; return false; }
-            B.i32v(pre ? -1 : cd->up); B.i32v(pre ? 0 : cd->lp);
-            B.u16v(pre ? 0 : cd->ucnt); B.u16v(pre ? 1 : cd->lcnt);
-            B.u16v(pre ? 0 : cd->a_cnt); B.u16v(chunk_cnt);
-            const i32 cover = kWideARegs * groups;          // A values the kernel keeps in registers
-            const i32 an_cnt = nx ? std::min(nx->a_cnt, cover) : 0;
-            B.u16v(R.ring); B.u16v(an_cnt);
-            B.u16v(fdst16); B.u16v(funits); B.i32v(fsrc16);
-            i32 pf_src = -1, pf_cnt = 0;
-            if (pf && pf->a_cnt > 0) {
-                i32 lo = INT32_MAX, hi = -1;
-                for (i32 t = 0; t < pf->a_cnt; ++t) { lo = std::min(lo, S.a_src[pf->a_ptr + t]); hi = std::max(hi, S.a_src[pf->a_ptr + t]); }
-                pf_src = lo; pf_cnt = std::min(hi - lo + 1, 0xffff);
-            }
-            B.i32v(pf_src); B.u16v(pf_cnt); B.u16v(0);
-            B.i32v(0); B.i32v(0); B.i32v(0);
-            if (!pre) for (i32 t = 0; t < cd->a_cnt; ++t) B.u16v((i64)(S.a_off[cd->a_ptr + t] * entry));
-            B.pad(4);
-            for (i32 t = 0; t < an_cnt; ++t) B.i32v(S.a_src[nx->a_ptr + t]);
-            if (!pre) for (i32 t = cover; t < cd->a_cnt; ++t) B.i32v(S.a_src[cd->a_ptr + t]);      // own overflow
-            B.pad(16);
-        } else {
-            B.i32v(fsrc16); B.u16v(fdst16); B.u16v(funits);
-            B.u16v(R.immediate ? 1 : 0); B.u16v(0); B.i32v(0);
-            // Entry order inside a chunk is free (the operations are independent).  Entries 2q and 2q+1 are served
-            // by the same shared-memory wavefront: give them targets in different halves of a 128-byte bank row
-            // (different slot parity for 64-byte entries) whenever possible, so the accumulator accesses are
-            // conflict-free.  An operation whose multiplier differs from the first half's goes last.
-            std::vector<Op> ord;
-            {
-                std::vector<Op> ev, od;
-                const size_t half = entry >= 128 ? 0 : 128 / entry;          // entries per bank row (0: no pairing needed)
-                for (const Op &o : R.ops) {
-                    const i32 tg = S.upd_map[(size_t)S.pairs[o.pair].mapstart + o.t];
-                    ((half && (tg % (i32)half) >= (i32)half / 2) ? od : ev).push_back(o);
+        // ---- phase 3: emit ---------------------------------------------------------------------------------------------
+        std::vector<std::vector<uint8_t>> blobs((size_t)nrec);
+        for (i32 r = 0; r < nrec; ++r) {
+            const Rec &R = recs[r];
+            std::vector<uint8_t> &b = blobs[r];
+            Bytes B(b);
+            const i64 fdst16 = (i64)((lsrc0 + R.fetch.dst) * entry / 16), funits = (i64)((size_t)R.fetch.len * entry / 16);
+            const i32 fsrc16 = (i32)((size_t)R.fetch.src * entry / 16);
+            if (R.kind == 0) {
+                const bool pre = R.group < 0;
+                const Group *g = pre ? nullptr : &G[R.group];
+                const Group *nx = (R.group + 1 < ngroups) ? &G[R.group + 1] : nullptr;
+                const Group *pf = (R.group + kWidePfGroups < ngroups && R.group + kWidePfGroups >= 0) ? &G[R.group + kWidePfGroups] : nullptr;
+                // A lists of a group: its columns one after the other
+                auto a_list = [&](const Group &gg, std::vector<std::pair<i32, i32>> &out) {       // (slot, src)
+                    for (size_t c = 0; c < gg.cols.size(); ++c) {
+                        const ColDesc &cd = S.cols[gg.cols[c]];
+                        for (i32 t = 0; t < cd.a_cnt; ++t) out.emplace_back(gg.base[c] + S.a_off[cd.a_ptr + t], S.a_src[cd.a_ptr + t]);
+                    }
+                };
+                std::vector<std::pair<i32, i32>> own, next;
+                if (g) a_list(*g, own);
+                if (nx) a_list(*nx, next);
+                const i32 an_cnt = std::min((i32)next.size(), cover);
+                B.i32v(0); B.i32v(0);
+                B.u16v(pre ? 0 : (i64)g->cols.size()); B.u16v(pre ? 0 : g->nslots);
+                B.u16v((i64)own.size()); B.u16v(pre ? 0 : g->chunk_cnt);
+                B.u16v(pre ? 0 : g->fin_cnt); B.u16v(an_cnt);
+                B.u16v(fdst16); B.u16v(funits); B.i32v(fsrc16);
+                B.u16v(pf ? (i64)pf->cols.size() : 0); B.u16v(0); B.u16v(0); B.u16v(0);
+                B.i32v(0); B.i32v(0); B.i32v(0);
+                for (i32 c = 0; c < kWideGroupCols; ++c) {
+                    if (g && c < (i32)g->cols.size()) {
+                        const ColDesc &cd = S.cols[g->cols[c]];
+                        B.i32v(g->cols[c] + 1); B.u16v((i64)((size_t)(g->base[c] + cd.ucnt - 1) * entry)); B.u16v(0);
+                    } else { B.i32v(0); B.u16v(0); B.u16v(0); }
                 }
-                size_t a = 0, b2 = 0;
-                while (a < ev.size() || b2 < od.size()) {
-                    if (a < ev.size()) ord.push_back(ev[a++]);
-                    if (b2 < od.size()) ord.push_back(od[b2++]);
+                for (i32 c = 0; c < kWideGroupCols; ++c) {
+                    i32 pf_src = -1, pf_cnt = 0;
+                    if (pf && c < (i32)pf->cols.size()) {
+                        const ColDesc &cd = S.cols[pf->cols[c]];
+                        i32 lo = INT32_MAX, hi = -1;
+                        for (i32 t = 0; t < cd.a_cnt; ++t) { lo = std::min(lo, S.a_src[cd.a_ptr + t]); hi = std::max(hi, S.a_src[cd.a_ptr + t]); }
+                        if (hi >= 0) { pf_src = lo; pf_cnt = hi - lo + 1; }
+                    }
+                    B.i32v(pf_src); B.i32v(pf_cnt);
+                }
+                for (auto &a : own) B.u16v((i64)((size_t)a.first * entry));
+                B.pad(4);
+                for (i32 t = 0; t < an_cnt; ++t) B.i32v(next[(size_t)t].second);
+                for (size_t t = (size_t)cover; t < own.size(); ++t) B.i32v(own[t].second);         // own overflow
+                B.pad(16);
+            } else if (R.kind == 1) {
+                B.i32v(fsrc16); B.u16v(fdst16); B.u16v(funits);
+                B.u16v(R.immediate ? 1 : 0); B.u16v(0); B.i32v(0);
+                // Entry order inside a chunk is free (the operations are independent).  Entries 2q and 2q+1 are
+                // served by the same shared-memory wavefront: give them targets in different halves of a 128-byte
+                // bank row whenever possible, so the accumulator accesses are conflict-free.
+                std::vector<Op> ord;
+                {
+                    std::vector<Op> ev, od;
+                    const size_t half = entry >= 128 ? 0 : 128 / entry;
+                    for (const Op &o : R.ops) {
+                        const i32 tg = o.base + S.upd_map[(size_t)S.pairs[o.pair].mapstart + o.t];
+                        ((half && (tg % (i32)half) >= (i32)half / 2) ? od : ev).push_back(o);
+                    }
+                    size_t a = 0, b2 = 0;
+                    while (a < ev.size() || b2 < od.size()) {
+                        if (a < ev.size()) ord.push_back(ev[a++]);
+                        if (b2 < od.size()) ord.push_back(od[b2++]);
+                    }
+                }
+                for (i32 u = 0; u < cap; ++u) {
+                    if (u < (i32)ord.size()) {
+                        const Op &o = ord[(size_t)u];
+                        const PairDesc &pd = S.pairs[o.pair];
+                        if (pair_src[o.pair] < 0) { *why = "wide refactor: internal error (unresolved source)"; return false; }
+                        B.u16v((i64)((lsrc0 + pair_src[o.pair] + o.t) * entry));
+                        B.u16v((i64)((size_t)(o.base + pd.moff) * entry));
+                        B.u16v((i64)((size_t)(o.base + S.upd_map[(size_t)pd.mapstart + o.t]) * entry));
+                        B.u16v(1);
+                    } else {
+                        B.u16v((i64)(lsrc0 * entry)); B.u16v(0); B.u16v(0); B.u16v(0);
+                    }
+                }
+                W.chunk_ops += (i64)R.ops.size();
+                ++W.chunks;
+            } else {
+                B.i32v(fsrc16); B.u16v(fdst16); B.u16v(funits);
+                B.u16v(0); B.u16v(0); B.i32v(0);
+                for (i32 u = 0; u < cap; ++u) {
+                    if (u < (i32)R.fins.size()) {
+                        const FinEnt &f = R.fins[(size_t)u];
+                        B.i32v(f.gout); B.u16v((i64)((size_t)f.slot * entry));
+                        B.u16v(f.cache >= 0 ? (i64)((lsrc0 + f.cache) * entry) : 0xffff);
+                    } else { B.i32v(0); B.u16v(0xffff); B.u16v(0xffff); }
                 }
             }
-            for (i32 u = 0; u < cap; ++u) {
-                if (u < (i32)ord.size()) {
-                    const Op &o = ord[(size_t)u];
-                    const PairDesc &pd = S.pairs[o.pair];
-                    if (pair_src[o.pair] < 0) { *why = "wide refactor: internal error (unresolved source)"; return false; }
-                    B.u16v((i64)(((size_t)acc_slots + pair_src[o.pair] + o.t) * entry));
-                    B.u16v((i64)(pd.moff * entry));
-                    B.u16v((i64)(S.upd_map[(size_t)pd.mapstart + o.t] * entry));
-                    B.u16v(1);
-                } else {
-                    B.u16v((i64)((size_t)acc_slots * entry)); B.u16v(0); B.u16v(0); B.u16v(0);
-                }
-            }
-            W.chunk_ops += (i64)R.ops.size();
-            ++W.chunks;
+            if (b.size() > max_rec || b.size() > stage) { *why = "wide refactor: internal error (record larger than planned)"; return false; }
         }
-        if (b.size() > max_rec) { *why = "wide refactor: internal error (record larger than planned)"; return false; }
-    }
-    size_t pos = 0, cur_stage = 0;
-    for (i32 r = 0; r < nrec; ++r) {
-        // flags of record r describe its own start (stages entered) and whether the NEXT record starts at the
-        // ring base
-        const size_t st = pos / stage;
-        const size_t adv = st - cur_stage;
-        cur_stage = st;
-        if (adv > 2) { *why = "wide refactor: internal error (stage skip)"; return false; }
-        size_t pad = 0;
-        bool wrap = false;
-        if (r + 1 < nrec) {
-            const size_t next_start = pos + blobs[r].size();
-            const size_t next_end = next_start + blobs[r + 1].size();
-            if (next_start / prog_ring != (next_end - 1) / prog_ring) { pad = round_up(next_start, prog_ring) - next_start; wrap = true; }
-            else if (next_start % prog_ring == 0) wrap = true;          // lands exactly on the ring base
+        std::vector<uint8_t> &out = W.prog.bytes;
+        size_t pos = 0, cur_stage = 0;
+        std::vector<size_t> rec_stage((size_t)nrec);
+        bool ok = true;
+        for (i32 r = 0; r < nrec && ok; ++r) {
+            const size_t st = pos / stage;
+            const size_t adv = st - cur_stage;
+            cur_stage = st;
+            rec_stage[r] = st;
+            if (adv > 2) { ok = false; break; }
+            size_t pad = 0;
+            bool wrap = false;
+            if (r + 1 < nrec) {
+                const size_t next_start = pos + blobs[r].size();
+                const size_t next_end = next_start + blobs[r + 1].size();
+                if (next_start / prog_ring != (next_end - 1) / prog_ring) { pad = round_up(next_start, prog_ring) - next_start; wrap = true; }
+                else if (next_start % prog_ring == 0) wrap = true;
+            }
+            const uint8_t fl = (uint8_t)((adv << 1) | (wrap ? 8 : 0));
+            blobs[r][recs[r].kind == 0 ? 34 : 8] |= fl;
+            out.insert(out.end(), blobs[r].begin(), blobs[r].end());
+            out.insert(out.end(), pad, 0);
+            pos = out.size();
         }
-        const uint8_t fl = (uint8_t)((adv << 1) | (wrap ? 8 : 0));
-        blobs[r][recs[r].is_col ? 34 : 8] |= fl;
-        out.insert(out.end(), blobs[r].begin(), blobs[r].end());
-        out.insert(out.end(), pad, 0);
-        pos = out.size();
+        // The reader requests stage t when it enters stage t - (kWideProgStages - 2) and first touches it up to two
+        // records before the first record that starts in it (headers are read ahead); the request rides in the cp.async
+        // group of its record and is only waited for kWideLookahead records later.  Check that on the real layout.
+        if (ok) {
+            std::vector<i32> first_in((size_t)cur_stage + 2, -1);
+            for (i32 r = nrec - 1; r >= 0; --r) first_in[rec_stage[r]] = r;
+            for (size_t t = (size_t)kWideProgStages - 1; t <= cur_stage && ok; ++t) {
+                if (first_in[t] < 0) continue;
+                size_t q = t - (size_t)(kWideProgStages - 2);        // the reader requests stage t when it passes stage q
+                while (q <= cur_stage && first_in[q] < 0) ++q;
+                const i32 a = first_in[q];
+                // first touch: one record before the first record of stage t (records are read one ahead, and that
+                // record may itself extend into t), relying on the wait of the record before: + 3 records of margin
+                if (first_in[t] - a < kWideLookahead + 4) ok = false;
+            }
+        }
+        if (!ok) continue;                                       // larger stages
+        while (out.size() % stage) out.push_back(0);
+        out.insert(out.end(), stage, 0);                          // guard stage
+        W.records = nrec; W.ngroups = ngroups;
+        if (getenv("CSP3_DEBUG")) {
+            i64 fins = 0;
+            for (const Group &g : G) fins += g.fin_cnt;
+            fprintf(stderr, "csp3: wide refactor: %d columns in %d groups, %lld chunk records (%.1f ops each), %lld finalisation records, %d records, stage %zu\n",
+                    n, ngroups, (long long)W.chunks, W.chunks ? (double)W.chunk_ops / (double)W.chunks : 0.0, (long long)fins, nrec, stage);
+        }
+        W.ok = true;
+        return true;
     }
-    while (out.size() % stage) out.push_back(0);
-    out.insert(out.end(), stage, 0);                          // guard stage
-    W.records = nrec;
-    W.ok = true;
-    return true;
+    *why = "wide refactor: program stream does not fit the ring";
+    return false;
 }
 
 }  // namespace csp3

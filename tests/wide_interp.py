@@ -40,7 +40,7 @@ def run_refactor(sym, Ax):
     ring_bytes = PROG_STAGES * stage
     B = Ax.shape[0]
     n, lnz, unz = sym.n, sym.lnz, sym.unz
-    nval = acc_slots + ring + land                    # value area, in entries: acc first, lsrc behind it
+    nval = acc_slots + 16 + ring + land               # value area, in entries: acc, pivot table, lsrc
     val = np.full((nval, B), np.nan)
     Lg = np.full((lnz, B), np.nan)
     Ug = np.full((unz, B), np.nan)
@@ -76,7 +76,7 @@ def run_refactor(sym, Ax):
         if units == 0:
             return
         flen, fdst, fsrc = entry_of(units * 16), entry_of(dst16 * 16), entry_of(src16 * 16)
-        assert fdst >= acc_slots + ring and fdst + flen <= nval, "fetch outside the landing area"
+        assert fdst >= acc_slots + 16 + ring and fdst + flen <= nval, "fetch outside the landing area"
         data = Lg[fsrc:fsrc + flen].copy()
         assert not np.isnan(data).any(), "fetch of an L column that is not final yet"
         val[fdst:fdst + flen] = np.nan
@@ -94,37 +94,45 @@ def run_refactor(sym, Ax):
                 keep.append((ready, dst, data))
         pending = keep
 
-    for c in range(n + 1):
-        (up, lp, ucnt, lcnt, a_cnt, pair_cnt, ringpos, an_cnt, fdst16, funits, fsrc16, pf_src, pf_cnt, flags) = \
-            struct.unpack_from("<iiHHHHHHHHiiHB", prog, p)
-        so = p + COL_HEADER
-        no = p + ((COL_HEADER + 2 * a_cnt + 3) & ~3)
+    GROUP_COLS = 8
+    table0 = acc_slots                                 # pivot / reciprocal entries live right behind the accumulator
+    lsrc0 = acc_slots + 2 * GROUP_COLS
+    cap = 2 * groups
+    cols_done = 0
+    first = True
+    while cols_done < n or first:
+        (ncols, nslots, a_cnt, chunk_cnt, fin_cnt, an_cnt, fdst16, funits, fsrc16, npf) = struct.unpack_from("<HHHHHHHHiH", prog, p + 8)
+        flags = prog[p + 34]
+        cdesc = np.frombuffer(prog, dtype=np.int32, count=2 * GROUP_COLS, offset=p + COL_HEADER).reshape(GROUP_COLS, 2)
+        pfd = np.frombuffer(prog, dtype=np.int32, count=2 * GROUP_COLS, offset=p + COL_HEADER + 8 * GROUP_COLS).reshape(GROUP_COLS, 2)
+        lists = COL_HEADER + 16 * GROUP_COLS
+        so = p + lists
+        no = p + ((lists + 2 * a_cnt + 3) & ~3)
         over = max(0, a_cnt - cover)
-        nbytes = (((COL_HEADER + 2 * a_cnt + 3) & ~3) + 4 * (an_cnt + over) + 15) & ~15
+        nbytes = (((lists + 2 * a_cnt + 3) & ~3) + 4 * (an_cnt + over) + 15) & ~15
         slots = [entry_of(int(v)) for v in np.frombuffer(prog, dtype=np.uint16, count=a_cnt, offset=so)]
         srcs = np.frombuffer(prog, dtype=np.int32, count=an_cnt + over, offset=no)
         p = advance(p, nbytes, flags)
         issue(funits, fdst16, fsrc16, False)
         land_ready()
-        ln = ucnt + lcnt - 1
-        assert ln <= acc_slots
-        val[:ln] = 0.0
-        if c == 0:
-            assert ucnt == 0 and a_cnt == 0 and pair_cnt == 0
-        k = c - 1
-        # scatter: register-held values first, then this column's own overflow entries
+        if first:
+            assert ncols == 0 and a_cnt == 0 and chunk_cnt == 0 and fin_cnt == 0
+            val[:acc_slots] = 0.0                      # the kernel clears the accumulator once
+        first = False
+        assert nslots <= acc_slots and ncols <= GROUP_COLS
+        assert (val[:acc_slots] == 0.0).all(), "accumulator not clean at the start of a group"
         for t in range(a_cnt):
-            assert slots[t] < ln
+            assert slots[t] < nslots
             if t < cover:
                 val[slots[t]] = an[t]
             else:
                 val[slots[t]] = AxT[srcs[an_cnt + t - cover]]
         an = [AxT[srcs[t]].copy() for t in range(an_cnt)]
-        if pf_src >= 0:
-            assert 0 <= pf_src and pf_src + pf_cnt <= sym.nnz
+        for c in range(npf):
+            if pfd[c, 0] >= 0:
+                assert 0 <= pfd[c, 0] and pfd[c, 0] + pfd[c, 1] <= sym.nnz
         rec_no += 1
-        cap = 2 * groups
-        for _ in range(pair_cnt):                      # chunk records of this column
+        for _ in range(chunk_cnt):
             fsrc16, fdst16, funits, flags = struct.unpack_from("<iHHH", prog, p)
             nbytes = CHUNK_HEADER + 8 * cap
             ent = np.frombuffer(prog, dtype=np.uint16, count=4 * cap, offset=p + CHUNK_HEADER).reshape(cap, 4)
@@ -136,26 +144,57 @@ def run_refactor(sym, Ax):
             src = np.array([entry_of(int(v)) for v in ent[ok, 0]])
             mul = np.array([entry_of(int(v)) for v in ent[ok, 1]])
             tgt = np.array([entry_of(int(v)) for v in ent[ok, 2]])
-            assert (src >= acc_slots).all() and (mul < ucnt).all() and (tgt < ln).all()
+            assert (src >= lsrc0).all() and (mul < nslots).all() and (tgt < nslots).all()
             assert len(set(tgt.tolist())) == len(tgt), "two operations of a chunk share a target"
             assert not (set(mul.tolist()) & set(tgt.tolist())), "a multiplier is modified inside its chunk"
             lv = val[src]
             assert not np.isnan(lv).any(), "chunk reads a source that has not landed (record %d)" % rec_no
             val[tgt] = val[tgt] - lv * val[mul]         # all loads, then all stores
-            stats["ops"] = stats.get("ops", 0) + int(ok.sum())
+            stats["ops"] += int(ok.sum())
             rec_no += 1
-        if ucnt > 0:
-            pivot = val[ucnt - 1].copy()
-            Ug[up:up + ucnt] = val[:ucnt]
-            Lg[lp] = 1.0
-            with np.errstate(all="ignore"):
-                v = val[ucnt:ucnt + lcnt - 1] / pivot
-            Lg[lp + 1:lp + lcnt] = v
-            if ringpos != 0xffff:
-                assert ringpos + lcnt - 1 <= ring
-                val[acc_slots + ringpos:acc_slots + ringpos + lcnt - 1] = v
-            bad = ~((np.abs(pivot) > 0) & np.isfinite(pivot))
-            fail = np.where((fail == 0) & bad, k + 1, fail)
+        # pivots of the group's columns (reciprocal pass), then the finalisation records
+        pivots = []
+        for c in range(ncols):
+            col1, w = int(cdesc[c, 0]), int(cdesc[c, 1]) & 0xffff
+            assert col1 > 0
+            pv = val[entry_of(w)].copy()
+            pivots.append(pv)
+            bad = ~((np.abs(pv) > 0) & np.isfinite(pv))
+            fail = np.where(bad & ((fail == 0) | (fail > col1)), col1, fail)
+        nfin = 0
+        for _ in range(fin_cnt):
+            fsrc16, fdst16, funits, flags = struct.unpack_from("<iHHH", prog, p)
+            nbytes = CHUNK_HEADER + 8 * cap
+            fe = np.frombuffer(prog, dtype=np.int32, count=2 * cap, offset=p + CHUNK_HEADER).reshape(cap, 2)
+            p = advance(p, nbytes, flags)
+            issue(funits, fdst16, fsrc16, False)
+            land_ready()
+            for u in range(cap):
+                gout, w = int(fe[u, 0]) & 0xffffffff, int(fe[u, 1]) & 0xffffffff
+                slot_off, cache_off = w & 0xffff, w >> 16
+                if slot_off == 0xffff:
+                    continue
+                sl = entry_of(slot_off)
+                x = val[sl].copy()
+                val[sl] = 0.0
+                pos = gout & 0x0fffffff
+                if gout & 0x80000000:
+                    cidx = (gout >> 28) & 7
+                    assert cidx < ncols
+                    with np.errstate(all="ignore"):
+                        q = x / pivots[cidx]
+                    Lg[pos] = q
+                    if cache_off != 0xffff:
+                        ce = entry_of(cache_off)
+                        assert lsrc0 <= ce < lsrc0 + ring
+                        val[ce] = q
+                else:
+                    Ug[pos] = x
+                nfin += 1
+            rec_no += 1
+        assert nfin == nslots
+        cols_done += ncols
+    Lg[sym.Lp[:-1]] = 1.0                              # the unit diagonal is implicit in the workspace layout
     stats["records"] = rec_no
     assert rec_no == nrec
     return np.ascontiguousarray(Lg.T), np.ascontiguousarray(Ug.T), fail, stats
