@@ -14,7 +14,7 @@ import numpy as np
 from csparse3_b200 import _lib
 
 LOOKAHEAD = 4
-AREGS = 2
+AREGS = 4
 COL_HEADER = 48
 CHUNK_HEADER = 16
 PROG_STAGES = 8
