@@ -94,7 +94,8 @@ constexpr int kSvHeader = 24;
 //        then the indices of this group's own entries beyond the register-held ones; pad to 16
 // Finalisation record (16-byte header + C entries of 8 bytes, C = 2 * lane groups; same size as a chunk record):
 //   +0   i32 fetch_src16  +4 u16 fetch_dst16     +6 u16 fetch_units (0: none)      (a look-ahead fetch, as in chunks)
-//   +8   u16 flags (bits 1-2 stages entered, bit 3 wrap)
+//   +8   u16 flags (bits 1-2 stages entered, bit 3 wrap, bit 4: the record holds L entries, otherwise U entries;
+//        a record never mixes the two)
 //   +16  C x { i32 gout, u16 slot_off, u16 cache_off }
 //        gout: bit 31 = L entry (value = slot / pivot of its column), bits 28-30 = index of the column inside the
 //        group, bits 0-27 = position in the bundle's L or U array; slot_off == 0xffff: no entry;

@@ -195,8 +195,9 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
                 }
                 if (any) { recs.push_back(ch); ++chunk_id; ++g.chunk_cnt; }
             }
-            // finalisation: cache the strict L part of every column, emit fixed-size finalisation records
-            std::vector<FinEnt> fe;
+            // finalisation: cache the strict L part of every column; fixed-size finalisation records, U entries (copy)
+            // and L entries (divide) in separate records so that the kernel's two paths never diverge inside a record
+            std::vector<FinEnt> fu, fl;
             for (size_t c = 0; c < g.cols.size(); ++c) {
                 const i32 k = g.cols[c];
                 const ColDesc &cd = S.cols[k];
@@ -209,22 +210,25 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
                     cur += len;
                     ring_pos[k] = pos;
                 }
-                for (i32 t = 0; t < cd.ucnt; ++t) fe.push_back({cd.up + t, g.base[c] + t, -1});
+                for (i32 t = 0; t < cd.ucnt; ++t) fu.push_back({cd.up + t, g.base[c] + t, -1});
                 for (i32 t = 0; t < cd.lcnt - 1; ++t)
-                    fe.push_back({(i32)(0x80000000u | ((uint32_t)c << 28) | (uint32_t)(cd.lp + 1 + t)), g.base[c] + cd.ucnt + t, pos >= 0 ? pos + t : -1});
+                    fl.push_back({(i32)(0x80000000u | ((uint32_t)c << 28) | (uint32_t)(cd.lp + 1 + t)), g.base[c] + cd.ucnt + t, pos >= 0 ? pos + t : -1});
             }
-            for (size_t o = 0; o < fe.size(); o += (size_t)cap) {
-                Rec fr; fr.kind = 2; fr.group = gi;
-                fr.fins.assign(fe.begin() + (long)o, fe.begin() + (long)std::min(fe.size(), o + (size_t)cap));
-                recs.push_back(fr);
-                ++g.fin_cnt;
+            for (int kind = 0; kind < 2; ++kind) {
+                const std::vector<FinEnt> &fe = kind ? fl : fu;
+                for (size_t o = 0; o < fe.size(); o += (size_t)cap) {
+                    Rec fr; fr.kind = 2; fr.group = gi;
+                    fr.fins.assign(fe.begin() + (long)o, fe.begin() + (long)std::min(fe.size(), o + (size_t)cap));
+                    recs.push_back(fr);
+                    ++g.fin_cnt;
+                }
             }
         }
         const i32 nrec = (i32)recs.size();
         // record after which column j's L entries are in global memory: the last finalisation record of its group
         std::vector<i32> final_rec((size_t)n, 0);
         for (i32 gi = 0; gi < ngroups; ++gi)
-            for (i32 k : G[gi].cols) final_rec[k] = G[gi].first_rec + G[gi].chunk_cnt + G[gi].fin_cnt;      // first record AFTER the group
+            for (i32 k : G[gi].cols) final_rec[k] = G[gi].first_rec + 1 + G[gi].chunk_cnt + G[gi].fin_cnt;  // first record AFTER the group
         std::vector<i32> last_use((size_t)S.pairs.size(), -1);
         for (i32 r = 0; r < nrec; ++r)
             for (const Op &o : recs[r].ops) if (pair_far[o.pair]) last_use[o.pair] = r;
@@ -387,7 +391,7 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
                 ++W.chunks;
             } else {
                 B.i32v(fsrc16); B.u16v(fdst16); B.u16v(funits);
-                B.u16v(0); B.u16v(0); B.i32v(0);
+                B.u16v((!R.fins.empty() && R.fins[0].gout < 0) ? 16 : 0); B.u16v(0); B.i32v(0);       // bit 4: L entries
                 for (i32 u = 0; u < cap; ++u) {
                     if (u < (i32)R.fins.size()) {
                         const FinEnt &f = R.fins[(size_t)u];

@@ -58,10 +58,10 @@ def test_wide_programs_config3_pattern():
 
 @pytest.mark.parametrize("order,tol", [(1, 1e-3), (2, 1.0), (0, 1.0), (3, 0.1)])
 def test_wide_programs_small_matrices(order, tol):
-    rng = np.random.default_rng(100 + order)
-    cases = [synth.laplacian_2d(7), synth.laplacian_3d(4), (1, np.array([0, 1], dtype=np.int32), np.array([0], dtype=np.int32), np.array([2.0]))]
-    for t in range(4):
-        n = int(rng.integers(2, 120))
+    rng = np.random.default_rng(order)                 # same matrices as tests/test_gpu_parity.py::test_lu_small_matrices_bit_exact
+    cases = [synth.laplacian_2d(9), synth.laplacian_3d(5), (1, np.array([0, 1], dtype=np.int32), np.array([0], dtype=np.int32), np.array([2.0]))]
+    for t in range(5):
+        n = int(rng.integers(2, 150))
         A = sp.csc_matrix(sp.random(n, n, density=min(1.0, 3.0 / n + 0.03), random_state=int(rng.integers(1 << 30)),
                                     format="csc") + sp.diags(rng.uniform(0.5, 2.0, n)))
         cases.append((n, A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()))

@@ -174,6 +174,7 @@ def run_refactor(sym, Ax):
                 slot_off, cache_off = w & 0xffff, w >> 16
                 if slot_off == 0xffff:
                     continue
+                assert bool(gout & 0x80000000) == bool(flags & 16), "finalisation record mixes U and L entries"
                 sl = entry_of(slot_off)
                 x = val[sl].copy()
                 val[sl] = 0.0
