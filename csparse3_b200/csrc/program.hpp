@@ -105,7 +105,8 @@ constexpr int kSvHeader = 24;
 // that are mutually independent (no two share a target, no multiplier is a target of the chunk), taken in order
 // from the column's update sequence (pair after pair in the stored topological order of U(:,k), entry after
 // entry), so executing "all loads, then all stores" per chunk reproduces the sequential result bit for bit.
-// Lane group e of the kernel executes entries e and e + C/2.
+// Lane group e of the kernel executes entries e and e + C/2 with ONE multiplier load: when both are valid they have
+// the same mult_off (they belong to the same source column).
 //   +0   i32 fetch_src16  +4 u16 fetch_dst16     +6 u16 fetch_units (0: none)
 //   +8   u16 flags: bit 0 = the fetch of THIS record must land before it is used (immediate),
 //                   bits 1-2 = stages entered, bit 3 = wrap                   +10..15 reserved

@@ -175,6 +175,9 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
             while (remaining > 0) {
                 Rec ch; ch.kind = 1; ch.group = gi;
                 bool any = false;
+                // the two entries of a lane group share one multiplier load: they must belong to the same pair, so a
+                // chunk holds at most `groups` lane groups' worth of (pair, up to two operations)
+                i32 lane_groups = 0, run_pair = -1, run_cnt = 0;
                 for (size_t c = 0; c < g.cols.size(); ++c) {
                     Cur &u = cs[c];
                     while (!fin_col[c]) {
@@ -182,11 +185,15 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
                         if (u.pi >= u.pend) { fin_col[c] = 1; --remaining; break; }
                         const PairDesc &pd = S.pairs[u.pi];
                         const i32 tgt = g.base[c] + S.upd_map[(size_t)pd.mapstart + u.t], mult = g.base[c] + pd.moff;
-                        if ((i32)ch.ops.size() >= cap || stamp_t[tgt] == chunk_id || stamp_t[mult] == chunk_id) break;
+                        const bool new_group = (u.pi != run_pair) || (run_cnt % 2 == 0);       // needs another lane group
+                        if ((new_group && lane_groups >= groups) || stamp_t[tgt] == chunk_id || stamp_t[mult] == chunk_id) break;
                         // at most one pair per chunk may bring in a new landing run (one fetch slot per record)
                         if (u.first_of_pair && pair_far[u.pi] && ch.new_far >= 0) break;
                         if (u.first_of_pair && pair_far[u.pi]) ch.new_far = u.pi;
                         u.first_of_pair = false;
+                        if (u.pi != run_pair) { run_pair = u.pi; run_cnt = 0; }
+                        if (run_cnt % 2 == 0) ++lane_groups;
+                        ++run_cnt;
                         ch.ops.push_back({u.pi, u.t, g.base[c]});
                         stamp_t[tgt] = chunk_id;
                         ++u.t;
@@ -357,26 +364,44 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
             } else if (R.kind == 1) {
                 B.i32v(fsrc16); B.u16v(fdst16); B.u16v(funits);
                 B.u16v(R.immediate ? 1 : 0); B.u16v(0); B.i32v(0);
-                // Entry order inside a chunk is free (the operations are independent).  Entries 2q and 2q+1 are
-                // served by the same shared-memory wavefront: give them targets in different halves of a 128-byte
-                // bank row whenever possible, so the accumulator accesses are conflict-free.
-                std::vector<Op> ord;
+                // Slot assignment.  Lane group e executes entries e and e + groups with ONE multiplier load, so both come
+                // from the same pair.  Entries 2q and 2q+1 of either half are served by the same shared-memory wavefront:
+                // the operations of a pair are handed out by target parity (lane group 2q gets even targets, 2q+1 odd
+                // ones) whenever possible, so the accumulator accesses are conflict-free.
+                std::vector<i32> slot_op((size_t)cap, -1);
                 {
-                    std::vector<Op> ev, od;
                     const size_t half = entry >= 128 ? 0 : 128 / entry;
-                    for (const Op &o : R.ops) {
-                        const i32 tg = o.base + S.upd_map[(size_t)S.pairs[o.pair].mapstart + o.t];
-                        ((half && (tg % (i32)half) >= (i32)half / 2) ? od : ev).push_back(o);
-                    }
-                    size_t a = 0, b2 = 0;
-                    while (a < ev.size() || b2 < od.size()) {
-                        if (a < ev.size()) ord.push_back(ev[a++]);
-                        if (b2 < od.size()) ord.push_back(od[b2++]);
+                    i32 lg = 0;
+                    size_t o = 0;
+                    while (o < R.ops.size()) {
+                        size_t o2 = o;
+                        while (o2 < R.ops.size() && R.ops[o2].pair == R.ops[o].pair) ++o2;
+                        std::vector<i32> ev, od;                               // operations of this pair by target parity
+                        for (size_t x = o; x < o2; ++x) {
+                            const i32 tg = R.ops[x].base + S.upd_map[(size_t)S.pairs[R.ops[x].pair].mapstart + R.ops[x].t];
+                            ((half && (tg % (i32)half) >= (i32)half / 2) ? od : ev).push_back((i32)x);
+                        }
+                        size_t a = 0, b2 = 0;
+                        while (a < ev.size() || b2 < od.size()) {
+                            // even lane groups prefer even targets, odd lane groups odd targets; two operations each
+                            std::vector<i32> &first = (lg % 2 == 0) ? ev : od, &second = (lg % 2 == 0) ? od : ev;
+                            size_t &fi = (lg % 2 == 0) ? a : b2, &si = (lg % 2 == 0) ? b2 : a;
+                            i32 take[2] = {-1, -1};
+                            for (int q = 0; q < 2; ++q) {
+                                if (fi < first.size()) take[q] = first[fi++];
+                                else if (si < second.size()) take[q] = second[si++];
+                            }
+                            if (lg >= groups) { *why = "wide refactor: internal error (lane groups)"; return false; }
+                            slot_op[(size_t)lg] = take[0];
+                            slot_op[(size_t)(lg + groups)] = take[1];
+                            ++lg;
+                        }
+                        o = o2;
                     }
                 }
                 for (i32 u = 0; u < cap; ++u) {
-                    if (u < (i32)ord.size()) {
-                        const Op &o = ord[(size_t)u];
+                    if (slot_op[(size_t)u] >= 0) {
+                        const Op &o = R.ops[(size_t)slot_op[(size_t)u]];
                         const PairDesc &pd = S.pairs[o.pair];
                         if (pair_src[o.pair] < 0) { *why = "wide refactor: internal error (unresolved source)"; return false; }
                         B.u16v((i64)((lsrc0 + pair_src[o.pair] + o.t) * entry));

@@ -141,6 +141,9 @@ def run_refactor(sym, Ax):
             land_ready()
             ok = ent[:, 3] != 0
             assert ok.any() and set(np.unique(ent[:, 3]).tolist()) <= {0, 1}
+            for e in range(groups):                    # one multiplier load per lane group (entries e and e + groups)
+                if ok[e + groups]:
+                    assert ok[e] and ent[e, 1] == ent[e + groups, 1], "entries of a lane group have different multipliers"
             src = np.array([entry_of(int(v)) for v in ent[ok, 0]])
             mul = np.array([entry_of(int(v)) for v in ent[ok, 1]])
             tgt = np.array([entry_of(int(v)) for v in ent[ok, 2]])
