@@ -114,10 +114,10 @@ constexpr int kSvHeader = 24;
 
 namespace csp3 {
 constexpr int kWideLookahead = 4;     // records between a fetch and its use == pending cp.async groups allowed
-constexpr int kWideARegs = 4;         // A values (per system) a lane holds in registers one group ahead
+constexpr int kWideARegs = 6;         // A values (per system) a lane holds in registers one group ahead
 constexpr int kWidePfGroups = 4;      // L2 prefetch distance of the A values, in groups
 constexpr int kWideGroupCols = 8;     // columns per group (one lane group each in the reciprocal pass)
-constexpr int kWideGroupA = 32;       // A entries per group of more than one column
+constexpr int kWideGroupA = 48;       // A entries per group of more than one column
 constexpr int kWideColHeader = 48;     // group record header
 constexpr int kWideChunkHeader = 16;
 constexpr int kWideProgStages = 8;      // ring slots of the program stream (see WideStream in lu_wide.cu)

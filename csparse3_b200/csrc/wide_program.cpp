@@ -124,7 +124,19 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
         return true;
     };
 
-    for (int attempt = 0; attempt < 4; ++attempt, stage *= 2) {
+    // Two chunk packers.  The list scheduler (mode 1) also places the landing runs itself; when it cannot make
+    // progress (landing area full of runs whose pairs wait for each other) the program is compiled again with the
+    // in-order packer (mode 0), whose runs are consumed one after the other.
+    static const int sched_env = getenv("CSP3_WIDE_SCHED") ? atoi(getenv("CSP3_WIDE_SCHED")) : 1;
+    static const int pair_window = getenv("CSP3_WIDE_PAIRS") ? std::max(1, atoi(getenv("CSP3_WIDE_PAIRS"))) : 3;
+    static const int run_cap_env = getenv("CSP3_WIDE_RUN") ? atoi(getenv("CSP3_WIDE_RUN")) : 0;
+    const size_t stage0 = stage;
+    for (int mode = sched_env ? 1 : 0; mode >= 0; --mode) {
+    const bool listsched = mode == 1;
+    const i32 run_cap = run_cap_env > 0 ? run_cap_env : std::max(max_llen, stage_entries / 5);
+    bool sched_failed = false;
+    stage = stage0;
+    for (int attempt = 0; attempt < 4 && !sched_failed; ++attempt, stage *= 2) {
         W = WideProgram();
         i32 ring_entries = 0;
         if (!geometry(stage, ring_entries)) { *why = "wide refactor working set exceeds the shared-memory budget"; return false; }
@@ -150,9 +162,28 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
         { Rec r; r.kind = 0; r.group = -1; recs.push_back(r); }
         std::vector<i32> stamp_t((size_t)acc_slots + 1, -1);     // accumulator slot -> chunk id that writes it
         i32 chunk_id = 0;
+        // record after which column j's L entries are in global memory: the first record AFTER its group
+        std::vector<i32> final_rec((size_t)n, 0);
+        // list scheduler: landing entry -> first record that may overwrite it (INT32_MAX while a run is in use)
+        std::vector<i32> free_at((size_t)stage_entries, 0);
+        i32 land_cur = 0;
+        long long dbg[4] = {0, 0, 0, 0};
+        auto land_alloc = [&](i32 len, i32 x) -> i32 {           // run of `len` entries writable from record x on
+            if (len > stage_entries) return -1;
+            for (int pass = 0; pass < 2; ++pass) {
+                const i32 lo = pass == 0 ? land_cur : 0, hi = pass == 0 ? stage_entries : std::min(stage_entries, land_cur + len - 1);
+                i32 run = 0;
+                for (i32 e = lo; e < hi; ++e) {
+                    run = free_at[(size_t)e] <= x ? run + 1 : 0;
+                    if (run >= len) { land_cur = e + 1; return e + 1 - len; }
+                }
+            }
+            return -1;
+        };
         for (i32 gi = 0; gi < ngroups; ++gi) {
             Group &g = G[gi];
             g.first_rec = (i32)recs.size();
+            g.chunk_cnt = g.fin_cnt = 0;
             { Rec r; r.kind = 0; r.group = gi; recs.push_back(r); }
             // per column: cursor over its pairs / entries
             struct Cur { i32 pi, pend, t; bool first_of_pair; };
@@ -169,6 +200,172 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
                     else { pair_far[pi] = 1; W.far_fma += pd.llen; }
                 }
             }
+            if (listsched) {
+            // chunks: list schedule of the group's update operations.  What must hold (and all that must hold) for the
+            // results to stay bit-identical: the operations on one accumulator slot run in their natural order, and a
+            // pair starts only when its multiplier is final, i.e. when nothing is left that targets the multiplier's
+            // slot (every such operation precedes the pair in natural order, because the pairs of a column are in
+            // topological order).  Ready operations are taken by height (longest dependent chain first); a column
+            // offers the operations of its first `pair_window` unfinished pairs only, which bounds the landing runs.
+            struct GOp { i32 pair, t, base, tgt, mult, height, next_same, col; };
+            std::vector<GOp> gops;
+            std::vector<i32> col_first(g.cols.size()), col_end(g.cols.size());
+            for (size_t c = 0; c < g.cols.size(); ++c) {
+                const ColDesc &cd = S.cols[g.cols[c]];
+                col_first[c] = cd.pair_ptr; col_end[c] = cd.pair_ptr + cd.pair_cnt;
+                for (i32 pi = cd.pair_ptr; pi < cd.pair_ptr + cd.pair_cnt; ++pi) {
+                    const PairDesc &pd = S.pairs[pi];
+                    for (i32 t = 0; t < pd.llen; ++t)
+                        gops.push_back({pi, t, g.base[c], g.base[c] + S.upd_map[(size_t)pd.mapstart + t], g.base[c] + pd.moff, 0, -1, (i32)c});
+                }
+            }
+            const i32 nops = (i32)gops.size();
+            std::vector<i32> head((size_t)g.nslots, -1), pending((size_t)g.nslots, 0);
+            {
+                std::vector<i32> hq((size_t)g.nslots, 0), hm((size_t)g.nslots, 0);
+                for (i32 o = nops - 1; o >= 0; --o) {
+                    GOp &u = gops[(size_t)o];
+                    u.height = 1 + std::max(hq[u.tgt], hm[u.tgt]);
+                    hq[u.tgt] = u.height;
+                    hm[u.mult] = std::max(hm[u.mult], u.height);
+                    u.next_same = head[u.tgt];
+                    head[u.tgt] = o;
+                    ++pending[u.tgt];
+                }
+            }
+            i32 pair_lo = INT32_MAX, pair_hi = -1;
+            for (size_t c = 0; c < g.cols.size(); ++c) { pair_lo = std::min(pair_lo, col_first[c]); pair_hi = std::max(pair_hi, col_end[c]); }
+            std::vector<char> started;                            // far pairs whose landing run is placed
+            std::vector<i32> pair_left;                           // operations a pair still has to go
+            if (pair_hi > pair_lo) { started.assign((size_t)(pair_hi - pair_lo), 0); pair_left.assign((size_t)(pair_hi - pair_lo), 0); }
+            for (const GOp &u : gops) ++pair_left[(size_t)(u.pair - pair_lo)];
+            struct Run1 { i32 start, len, left; };                // landing run: entries and operations still to read it
+            std::vector<Run1> runs;
+            std::vector<i32> run_of(pair_left.size(), -1), pair_owner(pair_left.size(), 0);
+            for (size_t c = 0; c < g.cols.size(); ++c) for (i32 pi = col_first[c]; pi < col_end[c]; ++pi) pair_owner[(size_t)(pi - pair_lo)] = (i32)c;
+            i32 left = nops;
+            std::vector<i32> ready;
+            struct Unit { i32 a, b, prio; };
+            std::vector<Unit> units, taken;
+            while (left > 0 && !sched_failed) {
+                Rec ch; ch.kind = 1; ch.group = gi;
+                const i32 r = (i32)recs.size();                   // index of this chunk record
+                // pair window of every column
+                std::vector<i32> limit(g.cols.size());
+                for (size_t c = 0; c < g.cols.size(); ++c) {
+                    while (col_first[c] < col_end[c] && pair_left[(size_t)(col_first[c] - pair_lo)] == 0) ++col_first[c];
+                    i32 seen = 0, pi = col_first[c];
+                    for (; pi < col_end[c] && seen < pair_window; ++pi) if (pair_left[(size_t)(pi - pair_lo)] > 0) ++seen;
+                    limit[c] = pi;
+                }
+                ready.clear();
+                for (i32 sl = 0; sl < g.nslots; ++sl) {
+                    const i32 o = head[(size_t)sl];
+                    if (o < 0) continue;
+                    const GOp &q = gops[(size_t)o];
+                    if (pending[(size_t)q.mult] == 0 && q.pair < limit[(size_t)q.col]) ready.push_back(o);
+                }
+                // lane-group units: up to two ready operations of one pair (they share the multiplier load)
+                std::sort(ready.begin(), ready.end(), [&](i32 x, i32 y) {
+                    const GOp &a1 = gops[(size_t)x], &b1 = gops[(size_t)y];
+                    if (a1.pair != b1.pair) return a1.pair < b1.pair;
+                    if (a1.height != b1.height) return a1.height > b1.height;
+                    return x < y;
+                });
+                units.clear();
+                for (size_t x = 0; x < ready.size();) {
+                    const bool two = x + 1 < ready.size() && gops[(size_t)ready[x + 1]].pair == gops[(size_t)ready[x]].pair;
+                    units.push_back({ready[x], two ? ready[x + 1] : -1, gops[(size_t)ready[x]].height});
+                    x += two ? 2 : 1;
+                }
+                std::stable_sort(units.begin(), units.end(), [&](const Unit &x, const Unit &y) {
+                    if (x.prio != y.prio) return x.prio > y.prio;
+                    return (x.b >= 0) > (y.b >= 0);
+                });
+                taken.clear();
+                // a new landing run: fetched by one of the records r - lookahead - 3 .. r - lookahead when the source
+                // column is final by then and a fetch slot and landing entries are free; an immediate fetch (the
+                // kernel waits for it) only when the chunk would otherwise be empty
+                auto place = [&](i32 pi, bool immediate) -> bool {
+                    // the run: this pair and, when the following pairs of the column take the next L columns (a
+                    // supernode-like chain), those too -- their values are adjacent in the workspace, one fetch
+                    const i32 c = pair_owner[(size_t)(pi - pair_lo)];
+                    i32 last = pi;
+                    const i32 src0 = S.pairs[pi].lstart;
+                    i32 len = S.pairs[pi].llen, need = final_rec[pair_col[pi]];
+                    if (!immediate) {
+                        for (i32 pn = pi + 1; pn < col_end[(size_t)c]; ++pn) {
+                            const PairDesc &pn_d = S.pairs[pn];
+                            if (pn_d.llen == 0 || !pair_far[pn] || started[(size_t)(pn - pair_lo)] || pair_col[pn] != pair_col[last] + 1) break;
+                            const i32 nlen = pn_d.lstart + pn_d.llen - src0;
+                            if (nlen > run_cap) break;
+                            len = nlen; last = pn;
+                            need = std::max(need, final_rec[pair_col[pn]]);
+                        }
+                    }
+                    i32 s0 = -1, x = -1;
+                    if (!immediate) {
+                        for (x = r - kWideLookahead; x >= std::max(0, r - kWideLookahead - 3); --x) {
+                            if (recs[(size_t)x].fetch.len != 0) { ++dbg[0]; continue; }
+                            if (need > x || need == 0) { ++dbg[1]; continue; }
+                            s0 = land_alloc(len, x);
+                            if (s0 < 0) { ++dbg[2]; continue; }
+                            break;
+                        }
+                        if (s0 < 0) return false;
+                        recs[(size_t)x].fetch.len = len; recs[(size_t)x].fetch.dst = ring_entries + s0; recs[(size_t)x].fetch.src = src0;
+                    } else {
+                        if (ch.fetch.len != 0) return false;
+                        s0 = land_alloc(len, r);
+                        if (s0 < 0) return false;
+                        ch.fetch.len = len; ch.fetch.dst = ring_entries + s0; ch.fetch.src = src0;
+                        ch.immediate = true;
+                        ++W.immediate_fetches;
+                    }
+                    for (i32 e = 0; e < len; ++e) free_at[(size_t)(s0 + e)] = INT32_MAX;
+                    runs.push_back({s0, len, 0});
+                    for (i32 pn = pi; pn <= last; ++pn) {
+                        if (S.pairs[pn].llen == 0) continue;
+                        pair_src[pn] = ring_entries + s0 + (S.pairs[pn].lstart - src0);
+                        started[(size_t)(pn - pair_lo)] = 1;
+                        run_of[(size_t)(pn - pair_lo)] = (i32)runs.size() - 1;
+                        runs.back().left += pair_left[(size_t)(pn - pair_lo)];
+                    }
+                    return true;
+                };
+                for (int force = 0; force < 2 && taken.empty(); ++force) {
+                    for (const Unit &u : units) {
+                        if ((i32)taken.size() >= groups) break;
+                        const i32 pi = gops[(size_t)u.a].pair;
+                        if (pair_far[pi] && !started[(size_t)(pi - pair_lo)]) {
+                            if (!place(pi, force != 0)) continue;
+                        }
+                        taken.push_back(u);
+                    }
+                }
+                if (taken.empty()) { sched_failed = true; break; }
+                // the emitter wants the operations of a pair next to each other
+                std::stable_sort(taken.begin(), taken.end(), [&](const Unit &x, const Unit &y) { return gops[(size_t)x.a].pair < gops[(size_t)y.a].pair; });
+                for (const Unit &u : taken) {
+                    for (i32 o : {u.a, u.b}) {
+                        if (o < 0) continue;
+                        const GOp &q = gops[(size_t)o];
+                        ch.ops.push_back({q.pair, q.t, q.base});
+                        head[(size_t)q.tgt] = q.next_same;
+                        --pending[(size_t)q.tgt];
+                        --left;
+                        --pair_left[(size_t)(q.pair - pair_lo)];
+                        if (pair_far[q.pair]) {
+                            Run1 &ru = runs[(size_t)run_of[(size_t)(q.pair - pair_lo)]];
+                            if (--ru.left == 0)                                   // the run may be overwritten from the next record on
+                                for (i32 e = 0; e < ru.len; ++e) free_at[(size_t)(ru.start + e)] = r + 1;
+                        }
+                    }
+                }
+                recs.push_back(ch); ++chunk_id; ++g.chunk_cnt;
+            }
+            if (sched_failed) break;
+            } else {
             // chunks: round robin over the columns, every column strictly in its own order
             size_t remaining = g.cols.size();
             std::vector<char> fin_col(g.cols.size(), 0);
@@ -202,6 +399,7 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
                 }
                 if (any) { recs.push_back(ch); ++chunk_id; ++g.chunk_cnt; }
             }
+            }
             // finalisation: cache the strict L part of every column; fixed-size finalisation records, U entries (copy)
             // and L entries (divide) in separate records so that the kernel's two paths never diverge inside a record
             std::vector<FinEnt> fu, fl;
@@ -230,17 +428,16 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
                     ++g.fin_cnt;
                 }
             }
+            for (i32 k : g.cols) final_rec[k] = g.first_rec + 1 + g.chunk_cnt + g.fin_cnt;   // == recs.size()
         }
+        if (sched_failed) break;
         const i32 nrec = (i32)recs.size();
-        // record after which column j's L entries are in global memory: the last finalisation record of its group
-        std::vector<i32> final_rec((size_t)n, 0);
-        for (i32 gi = 0; gi < ngroups; ++gi)
-            for (i32 k : G[gi].cols) final_rec[k] = G[gi].first_rec + 1 + G[gi].chunk_cnt + G[gi].fin_cnt;  // first record AFTER the group
         std::vector<i32> last_use((size_t)S.pairs.size(), -1);
         for (i32 r = 0; r < nrec; ++r)
             for (const Op &o : recs[r].ops) if (pair_far[o.pair]) last_use[o.pair] = r;
 
-        // ---- phase 2: landing-area allocation in issue order ---------------------------------------------------------
+        // ---- phase 2 (in-order packer only): landing-area allocation in issue order -----------------------------------
+        if (!listsched) {
         struct Run { i32 pair, start, len; };
         std::vector<Run> live;
         i32 scur = 0;
@@ -308,6 +505,7 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
             }
         }
         if (failed) { *why = "wide refactor: landing area too small"; return false; }
+        }
 
         // ---- phase 3: emit ---------------------------------------------------------------------------------------------
         std::vector<std::vector<uint8_t>> blobs((size_t)nrec);
@@ -474,13 +672,17 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
         if (getenv("CSP3_DEBUG")) {
             i64 fins = 0;
             for (const Group &g : G) fins += g.fin_cnt;
-            fprintf(stderr, "csp3: wide refactor: %d columns in %d groups, %lld chunk records (%.1f ops each), %lld finalisation records, %d records, stage %zu\n",
-                    n, ngroups, (long long)W.chunks, W.chunks ? (double)W.chunk_ops / (double)W.chunks : 0.0, (long long)fins, nrec, stage);
+            fprintf(stderr, "place failures: slot %lld notfinal %lld landing %lld\n", dbg[0], dbg[1], dbg[2]);
+            fprintf(stderr, "csp3: wide refactor: %d columns in %d groups, %lld chunk records (%.1f ops each), %lld finalisation records, %d records, stage %zu, %s packer, %d immediate fetches\n",
+                    n, ngroups, (long long)W.chunks, W.chunks ? (double)W.chunk_ops / (double)W.chunks : 0.0, (long long)fins, nrec, stage,
+                    listsched ? "list" : "in-order", W.immediate_fetches);
         }
         W.ok = true;
         return true;
     }
-    *why = "wide refactor: program stream does not fit the ring";
+    if (!sched_failed) { *why = "wide refactor: program stream does not fit the ring"; return false; }
+    }
+    *why = "wide refactor: internal error (scheduler)";
     return false;
 }
 

@@ -14,7 +14,7 @@ import numpy as np
 from csparse3_b200 import _lib
 
 LOOKAHEAD = 4
-AREGS = 4
+AREGS = 6
 COL_HEADER = 48
 CHUNK_HEADER = 16
 PROG_STAGES = 8
@@ -44,7 +44,8 @@ def run_refactor(sym, Ax):
     val = np.full((nval, B), np.nan)
     Lg = np.full((lnz, B), np.nan)
     Ug = np.full((unz, B), np.nan)
-    AxT = np.ascontiguousarray(Ax.T)
+    Lg[sym.Lp[:-1]] = 1.0                              # unit diagonal: never written by the kernel, but a fetch of several
+    AxT = np.ascontiguousarray(Ax.T)                   # adjacent L columns reads across it (the value is not used)
     pending = []                       # (ready_record, dst entry, data)
     rec_no = 0
     p = 0
