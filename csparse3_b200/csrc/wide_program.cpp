@@ -62,6 +62,8 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
     i32 max_llen = 1, max_acnt = 0;
     for (const PairDesc &pd : S.pairs) max_llen = std::max(max_llen, pd.llen);
     for (const ColDesc &cd : S.cols) max_acnt = std::max(max_acnt, cd.a_cnt);
+    static const int ga_env = getenv("CSP3_WIDE_GA") ? atoi(getenv("CSP3_WIDE_GA")) : 0;
+    const i32 group_a_limit = ga_env > 0 ? std::min<i32>(ga_env, kWideGroupA) : kWideGroupA;
     const i32 group_a = std::max<i32>(kWideGroupA, max_acnt);
     // ---- record sizes -> program stage size ----------------------------------------------------------------
     const size_t chunk_rec = (size_t)kWideChunkHeader + 8 * (size_t)cap;
@@ -95,7 +97,7 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
                 bool ready = true;
                 for (i32 p = Up[k]; p < Up[k + 1] - 1 && ready; ++p) ready = done[Ui[p]] && !in_group[Ui[p]];
                 if (!ready) continue;
-                if (!g.cols.empty() && (g.nslots + len > acc_slots || a_total + cd.a_cnt > kWideGroupA)) continue;
+                if (!g.cols.empty() && (g.nslots + len > acc_slots || a_total + cd.a_cnt > group_a_limit)) continue;
                 g.cols.push_back(k); g.base.push_back(g.nslots);
                 g.nslots += len; a_total += cd.a_cnt;
                 in_group[k] = 1;
@@ -128,7 +130,7 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
     // progress (landing area full of runs whose pairs wait for each other) the program is compiled again with the
     // in-order packer (mode 0), whose runs are consumed one after the other.
     static const int sched_env = getenv("CSP3_WIDE_SCHED") ? atoi(getenv("CSP3_WIDE_SCHED")) : 1;
-    static const int pair_window = getenv("CSP3_WIDE_PAIRS") ? std::max(1, atoi(getenv("CSP3_WIDE_PAIRS"))) : 3;
+    static const int pair_window = getenv("CSP3_WIDE_PAIRS") ? std::max(1, atoi(getenv("CSP3_WIDE_PAIRS"))) : 4;
     static const int run_cap_env = getenv("CSP3_WIDE_RUN") ? atoi(getenv("CSP3_WIDE_RUN")) : 0;
     const size_t stage0 = stage;
     for (int mode = sched_env ? 1 : 0; mode >= 0; --mode) {
@@ -167,7 +169,6 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
         // list scheduler: landing entry -> first record that may overwrite it (INT32_MAX while a run is in use)
         std::vector<i32> free_at((size_t)stage_entries, 0);
         i32 land_cur = 0;
-        long long dbg[4] = {0, 0, 0, 0};
         auto land_alloc = [&](i32 len, i32 x) -> i32 {           // run of `len` entries writable from record x on
             if (len > stage_entries) return -1;
             for (int pass = 0; pass < 2; ++pass) {
@@ -306,11 +307,9 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
                     i32 s0 = -1, x = -1;
                     if (!immediate) {
                         for (x = r - kWideLookahead; x >= std::max(0, r - kWideLookahead - 3); --x) {
-                            if (recs[(size_t)x].fetch.len != 0) { ++dbg[0]; continue; }
-                            if (need > x || need == 0) { ++dbg[1]; continue; }
+                            if (recs[(size_t)x].fetch.len != 0 || need > x || need == 0) continue;   // slot taken / source not final
                             s0 = land_alloc(len, x);
-                            if (s0 < 0) { ++dbg[2]; continue; }
-                            break;
+                            if (s0 >= 0) break;
                         }
                         if (s0 < 0) return false;
                         recs[(size_t)x].fetch.len = len; recs[(size_t)x].fetch.dst = ring_entries + s0; recs[(size_t)x].fetch.src = src0;
@@ -672,7 +671,6 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
         if (getenv("CSP3_DEBUG")) {
             i64 fins = 0;
             for (const Group &g : G) fins += g.fin_cnt;
-            fprintf(stderr, "place failures: slot %lld notfinal %lld landing %lld\n", dbg[0], dbg[1], dbg[2]);
             fprintf(stderr, "csp3: wide refactor: %d columns in %d groups, %lld chunk records (%.1f ops each), %lld finalisation records, %d records, stage %zu, %s packer, %d immediate fetches\n",
                     n, ngroups, (long long)W.chunks, W.chunks ? (double)W.chunk_ops / (double)W.chunks : 0.0, (long long)fins, nrec, stage,
                     listsched ? "list" : "in-order", W.immediate_fetches);

@@ -242,7 +242,8 @@ def test_lu_grid118_bundle_widths_agree(path, S):
 
 
 @pytest.mark.parametrize("env", [{}, {"CSP3_WIDE_S": "16"}, {"CSP3_WIDE_S": "4"}, {"CSP3_WIDE_S": "16", "CSP3_WIDE_LANE": "4"},
-                                 {"CSP3_WIDE_F": "32"}, {"CSP3_WIDE_SOLVE": "0"}, {"CSP3_WIDE": "0"}])
+                                 {"CSP3_WIDE_F": "32"}, {"CSP3_WIDE_SOLVE": "0"}, {"CSP3_WIDE": "0"},
+                                 {"CSP3_WIDE_SCHED": "0"}, {"CSP3_WIDE_PAIRS": "16", "CSP3_WIDE_RUN": "64"}])
 def test_lu_wide_geometries_agree(env):
     """The wide (lane = system) kernels for several bundle widths / systems per lane, a tiny landing area (immediate
     fetches), wide refactor + v3 solve, and v3 only: all bit-identical to the oracle on a ragged batch; one system."""

@@ -90,10 +90,14 @@ def test_wide_refactor_reports_bad_pivots():
 
 
 @pytest.mark.parametrize("env", [{"CSP3_WIDE_S": "16"}, {"CSP3_WIDE_S": "4"}, {"CSP3_WIDE_S": "16", "CSP3_WIDE_LANE": "4"},
-                                 {"CSP3_WIDE_F": "32"}, {"CSP3_WIDE_R": "24", "CSP3_WIDE_F": "64"}])
+                                 {"CSP3_WIDE_F": "32"}, {"CSP3_WIDE_R": "24", "CSP3_WIDE_F": "64"},
+                                 {"CSP3_WIDE_SCHED": "0"}, {"CSP3_WIDE_SCHED": "0", "CSP3_WIDE_F": "32"},
+                                 {"CSP3_WIDE_PAIRS": "1"}, {"CSP3_WIDE_PAIRS": "16", "CSP3_WIDE_RUN": "64"},
+                                 {"CSP3_WIDE_GA": "16"}])
 def test_wide_programs_other_geometries(env):
-    """Bundle widths, 4 systems per lane, tiny landing area (immediate fetches) and tiny L cache: the knobs are read
-    once per process, so each setting runs in a child process."""
+    """Bundle widths, 4 systems per lane, tiny landing area (immediate fetches) and tiny L cache; the in-order chunk
+    packer (the list scheduler's fallback), pair windows, long landing runs, small groups: the knobs are read once
+    per process, so each setting runs in a child process."""
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import numpy as np; "
             "import test_wide_programs as t; from csparse3_b200 import synth; g = synth.GridCase(118); "
             "n, Ap, Ai, Ax0 = g.base_jacobian(); Axb, bb = g.jacobian_batch(0, 3); t._check(n, Ap, Ai, Axb, bb); print('ok')"
