@@ -40,6 +40,12 @@ SIGNATURES = {
     "csp3_spgemm_symbolic": [i64, i64, vp, vp, i64, i64, vp, vp, vp, C.POINTER(i64), vp],
     "csp3_spgemm_numeric": [i64, i64, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp],
     "csp3_csc_plusminus_host": [i64, i64, vp, vp, vp, vp, vp, vp, f64, vp, vp, vp],
+    "csp3_stack4_create": [i64, i64, vp, vp, i64, i64, vp, vp, i64, i64, vp, vp, i64, i64, vp, vp, C.POINTER(vp)],
+    "csp3_stack4_destroy": [vp],
+    "csp3_stack4_sizes": [vp, vp],
+    "csp3_stack4_get_pattern": [vp, vp, vp],
+    "csp3_stack4_batched": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp],
+    "csp3_csc_stack_4_by_4_host": [i64, i64, vp, vp, vp, i64, i64, vp, vp, vp, i64, i64, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp],
     "csp3_csc_amd": [i64, i64, i64, vp, vp, vp],
     "csp3_csc_etree": [i64, i64, vp, vp, cint, vp],
     "csp3_csc_post": [i64, vp, vp],

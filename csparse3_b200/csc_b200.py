@@ -10,7 +10,7 @@ buffers, exactly like the numba kernels take them; device-resident batched work 
 csparse3_b200.lu / csparse3_b200.spmv instead.  dtype strictness follows the reference's eager numba
 signatures (i8 scalars, i4[:] indices, f8[:] values).
 
-The last block of helpers (dense conversion, diagonals, stacking, sub-matrices, islands) is host-side
+The last block of helpers (dense conversion, diagonals, sub-matrices, islands) is host-side
 assembly glue that the reference also runs outside the numeric loop; it is plain numpy and never used by
 the refactor / solve / multiply path.
 """
@@ -250,27 +250,22 @@ def csc_diagonal_from_array(m, array):
 
 def csc_stack_4_by_4_ff(am, an, Ai, Ap, Ax, bm, bn, Bi, Bp, Bx, cm, cn, Ci, Cp, Cx, dm, dn, Di, Dp, Dx):
     """[[A, B], [C, D]] -> (m, n, indices, indptr, data).  csc_numba.py:640-720 (argument order indices,
-    indptr, data; column-wise concatenation, A's entries before C's inside a column)."""
+    indptr, data; column-wise concatenation, A's entries before C's inside a column).  CUDA: the pattern is
+    laid out by libcsparse3_b200's plan, the values are gathered on the device (csp3_csc_stack_4_by_4_host);
+    device-resident batches use csparse3_b200.assemble.Stack4Plan."""
     assert am == bm and cm == dm and an == cn and bn == dn
-
-    def half(n_, Tp, Ti, Tx, Bp_, Bi_, Bx_, off):
-        Tp, Bp_ = np.asarray(Tp, dtype=np.int64), np.asarray(Bp_, dtype=np.int64)
-        tc, bc = np.diff(Tp[:n_ + 1]), np.diff(Bp_[:n_ + 1])
-        ptr_ = np.concatenate([[0], np.cumsum(tc + bc)])
-        idx = np.empty(ptr_[-1], dtype=np.int32)
-        dat = np.empty(ptr_[-1], dtype=np.float64)
-        tcol = np.repeat(np.arange(n_), tc)
-        bcol = np.repeat(np.arange(n_), bc)
-        tpos = ptr_[tcol] + (np.arange(Tp[n_]) - Tp[tcol])
-        bpos = ptr_[bcol] + tc[bcol] + (np.arange(Bp_[n_]) - Bp_[bcol])
-        idx[tpos] = np.asarray(Ti)[:Tp[n_]]; dat[tpos] = np.asarray(Tx)[:Tp[n_]]
-        idx[bpos] = np.asarray(Bi_)[:Bp_[n_]] + off; dat[bpos] = np.asarray(Bx_)[:Bp_[n_]]
-        return ptr_, idx, dat
-
-    lp, li, lx = half(an, Ap, Ai, Ax, Cp, Ci, Cx, am)
-    rp, ri, rx = half(bn, Bp, Bi, Bx, Dp, Di, Dx, bm)
-    indptr = np.concatenate([lp, lp[-1] + rp[1:]]).astype(np.int32)
-    return am + cm, an + bn, np.concatenate([li, ri]), indptr, np.concatenate([lx, rx])
+    Ai, Ap, Ax = as_i32(Ai, "Ai"), as_i32(Ap, "Ap"), as_f64(Ax, "Ax")
+    Bi, Bp, Bx = as_i32(Bi, "Bi"), as_i32(Bp, "Bp"), as_f64(Bx, "Bx")
+    Ci, Cp, Cx = as_i32(Ci, "Ci"), as_i32(Cp, "Cp"), as_f64(Cx, "Cx")
+    Di, Dp, Dx = as_i32(Di, "Di"), as_i32(Dp, "Dp"), as_f64(Dx, "Dx")
+    nnz = int(Ap[an]) + int(Bp[bn]) + int(Cp[cn]) + int(Dp[dn])
+    indices = np.empty(nnz, dtype=np.int32)
+    indptr = np.empty(an + bn + 1, dtype=np.int32)
+    data = np.empty(nnz, dtype=np.float64)
+    check(_lib.lib().csp3_csc_stack_4_by_4_host(am, an, ptr(Ai), ptr(Ap), ptr(Ax), bm, bn, ptr(Bi), ptr(Bp), ptr(Bx),
+                                                cm, cn, ptr(Ci), ptr(Cp), ptr(Cx), dm, dn, ptr(Di), ptr(Dp), ptr(Dx),
+                                                ptr(indices), ptr(indptr), ptr(data)), "csc_stack_4_by_4_ff")
+    return am + cm, an + bn, indices, indptr, data
 
 
 def csc_sub_matrix_cols(Am, Anz, Ap, Ai, Ax, cols):

@@ -102,6 +102,38 @@ int csp3_csc_plusminus_host(int64_t m, int64_t n, const int32_t *Ap, const int32
                             const int32_t *Bp, const int32_t *Bi, const double *Bx, double sign, int32_t *Cp,
                             int32_t *Ci, double *Cx);
 
+/* ---- [[A, B], [C, D]]: Jacobian assembly ------------------------------------------------------------------- */
+/* Replaces csc_stack_4_by_4_ff, src/CSparse3/csc_numba.py:640-720 (caller pack_4_by_4, src/CSparse3/csc.py:588-606).
+ * Argument order as in the reference: (m, n, indices, indptr[, data]) per block.  Column-wise concatenation, the
+ * upper block's entries before the lower block's inside a column, lower row indices shifted by the upper block's
+ * row count; nothing is sorted or merged.  Shapes must satisfy am == bm, cm == dm, an == cn, bn == dn (the
+ * reference's assertions, csc_numba.py:679-682) or CSP3_ERR_ARG is returned.
+ *
+ * A plan holds the pattern work (host arrays in, done once per pattern); csp3_stack4_batched is the numeric step
+ * on the device for `batch` value sets sharing the four patterns:
+ *     out[s * ldo + p] = X_block(p)[s * ld_block + pos(p)],   p < nnz = nnzA + nnzB + nnzC + nnzD
+ * Ax..Dx, out are DEVICE pointers; ld* are the distances (in doubles) between the value sets of a block, 0 = one
+ * value set shared by the whole batch (e.g. a constant block).  The call is stream-ordered. */
+typedef struct csp3_stack4 csp3_stack4;
+int csp3_stack4_create(int64_t am, int64_t an, const int32_t *Ai, const int32_t *Ap,
+                       int64_t bm, int64_t bn, const int32_t *Bi, const int32_t *Bp,
+                       int64_t cm, int64_t cn, const int32_t *Ci, const int32_t *Cp,
+                       int64_t dm, int64_t dn, const int32_t *Di, const int32_t *Dp, csp3_stack4 **plan);
+int csp3_stack4_destroy(csp3_stack4 *plan);
+/* out[0..2] = m, n, nnz of the stacked matrix; out[4..7] = nnz of A, B, C, D */
+int csp3_stack4_sizes(const csp3_stack4 *plan, int64_t out[8]);
+/* indices[nnz], indptr[n+1] of the stacked matrix (host arrays) */
+int csp3_stack4_get_pattern(const csp3_stack4 *plan, int32_t *indices, int32_t *indptr);
+int csp3_stack4_batched(csp3_stack4 *plan, int64_t batch, const double *Ax, int64_t lda, const double *Bx, int64_t ldb,
+                        const double *Cx, int64_t ldc, const double *Dx, int64_t ldd, double *out, int64_t ldo,
+                        void *stream);
+/* One matrix, host arrays in and out (the reference's call): indices[nnz], indptr[an+bn+1], data[nnz]. */
+int csp3_csc_stack_4_by_4_host(int64_t am, int64_t an, const int32_t *Ai, const int32_t *Ap, const double *Ax,
+                               int64_t bm, int64_t bn, const int32_t *Bi, const int32_t *Bp, const double *Bx,
+                               int64_t cm, int64_t cn, const int32_t *Ci, const int32_t *Cp, const double *Cx,
+                               int64_t dm, int64_t dn, const int32_t *Di, const int32_t *Dp, const double *Dx,
+                               int32_t *indices, int32_t *indptr, double *data);
+
 /* ---- host symbolic phase (runs once per pattern, cached by the caller) ---------------------------------- */
 /* q = amd(order, A): CSparse cs_amd.  order 0 natural, 1 A+A', 2 S'S (dense rows dropped), 3 A'A.  q[n]. */
 int csp3_csc_amd(int64_t order, int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, int32_t *q);

@@ -346,3 +346,113 @@ def test_flat_lu_api_and_cscmat_solve():
                           orc.csc_lu_solve(n, Lp, Li, oL, Up, Ui, oU, pinv, q, b))
     A = CscMat(n, n, indptr=Ap, indices=Ai, data=Ax)
     assert np.array_equal(A.solve(b), orc.csc_lusol(1, n, Ap, Ai, Ax, b, 1e-3))
+
+
+# ---- [[A, B], [C, D]] assembly ---------------------------------------------------------
+
+def test_stack_matches_reference_fixture(golden_ref):
+    """csc_stack_4_by_4_ff against the output of the reference's numba kernel (tests/golden/make_golden.py)."""
+    d = golden_ref
+    args = []
+    for c in "abcd":
+        sh = d["st_" + c + "shape"]
+        args += [int(sh[0]), int(sh[1]), d["st_" + c + "i"], d["st_" + c + "p"], d["st_" + c + "x"]]
+    mm, nn, Pi, Pp, Px = B.csc_stack_4_by_4_ff(*args)
+    assert (mm, nn) == tuple(d["ref_st_shape"])
+    assert np.array_equal(Pi, d["ref_st_i"]) and np.array_equal(Pp, d["ref_st_p"]) and np.array_equal(Px, d["ref_st_x"])
+    oo = orc.csc_stack_4_by_4_ff(*args)
+    assert np.array_equal(Pi, oo[2]) and np.array_equal(Pp, oo[3]) and np.array_equal(Px, oo[4])
+
+
+def test_pack_4_by_4_vs_scipy():
+    """src/test/test_matrix_stacking.py:12-40 at a small seeded size."""
+    from csparse3_b200 import pack_4_by_4
+    k = 15
+    Q = [sp.csc_matrix(sp.random(*s, density=0.2, random_state=t)) for t, s in
+         enumerate([(k, 4 * k), (k, k), (6 * k, 4 * k), (6 * k, k)])]
+    E = sp.hstack((sp.vstack((Q[0], Q[2])), sp.vstack((Q[1], Q[3]))))
+    E1 = pack_4_by_4(*[scipy_to_mat(M) for M in Q])
+    assert (E.toarray() == E1.todense()).all()
+
+
+def test_stack_edge_cases():
+    """Empty blocks, empty columns, a block without columns; shape mismatch raises like the reference's assert."""
+    z = lambda m, n: scipy_to_mat(sp.csc_matrix((m, n)))
+    r = lambda m, n, s: scipy_to_mat(sp.csc_matrix(sp.random(m, n, density=0.3, random_state=s)))
+    for blocks in ([z(3, 4), z(3, 2), z(5, 4), z(5, 2)], [r(3, 4, 1), z(3, 2), z(5, 4), r(5, 2, 2)],
+                   [r(3, 4, 3), r(3, 0, 4), r(2, 4, 5), r(2, 0, 6)], [r(0, 3, 7), r(0, 2, 8), r(4, 3, 9), r(4, 2, 10)]):
+        args = []
+        for M in blocks:
+            args += [M.m, M.n, M.indices, M.indptr, M.data]
+        got = B.csc_stack_4_by_4_ff(*args)
+        want = orc.csc_stack_4_by_4_ff(*args)
+        assert got[:2] == want[:2]
+        for a, b in zip(got[2:], want[2:]):
+            assert np.array_equal(a, b)
+    with pytest.raises(AssertionError):
+        B.csc_stack_4_by_4_ff(3, 4, *[np.zeros(0, np.int32), np.zeros(5, np.int32), np.zeros(0)],
+                              2, 2, *[np.zeros(0, np.int32), np.zeros(3, np.int32), np.zeros(0)],
+                              5, 4, *[np.zeros(0, np.int32), np.zeros(5, np.int32), np.zeros(0)],
+                              5, 2, *[np.zeros(0, np.int32), np.zeros(3, np.int32), np.zeros(0)])
+
+
+def _jacobian_blocks(g, count):
+    """The four blocks of the polar Jacobian of `count` value sets, as (pattern CscMat x4, values [count, nnz] x4),
+    cut out of the assembled matrices of the generator (so that the stacked result is known)."""
+    n, Ap, Ai, Ax0 = g.base_jacobian()
+    Axb, bb = g.jacobian_batch(0, count)
+    J = sp.csc_matrix((np.arange(1, len(Ai) + 1, dtype=np.float64), Ai, Ap), shape=(n, n))      # entry numbers
+    n1 = n // 2 + 3                                     # any split point works for the stacking identity
+    blocks, vals = [], []
+    for rs, cs in ((slice(0, n1), slice(0, n1)), (slice(0, n1), slice(n1, n)), (slice(n1, n), slice(0, n1)), (slice(n1, n), slice(n1, n))):
+        S = sp.csc_matrix(J[rs, cs])
+        S.sort_indices()
+        src = S.data.astype(np.int64) - 1
+        blocks.append(CscMat(S.shape[0], S.shape[1], indptr=S.indptr.astype(np.int32), indices=S.indices.astype(np.int32),
+                             data=Ax0[src].copy()))
+        vals.append(np.ascontiguousarray(Axb[:, src]))
+    return (n, Ap, Ai, Ax0, Axb, bb), blocks, vals
+
+
+def test_stack4_plan_batched_vs_oracle():
+    """Device-resident batch: one gather kernel; every system equals the oracle's stacking of its four blocks, and
+    the stacked pattern is the Jacobian's own (sorted blocks of a sorted matrix)."""
+    import torch
+    from csparse3_b200.assemble import Stack4Plan
+    g = synth.GridCase(118)
+    (n, Ap, Ai, Ax0, Axb, bb), blocks, vals = _jacobian_blocks(g, 37)
+    plan = Stack4Plan(*blocks)
+    assert (plan.m, plan.n, plan.nnz) == (n, n, len(Ai))
+    assert np.array_equal(plan.indptr, Ap) and np.array_equal(plan.indices, Ai)
+    out = plan.assemble(*[torch.as_tensor(v).cuda() for v in vals]).cpu().numpy()
+    for s in (0, 5, 36):
+        args = []
+        for M, v in zip(blocks, vals):
+            args += [M.m, M.n, M.indices, M.indptr, v[s]]
+        want = orc.csc_stack_4_by_4_ff(*args)
+        assert np.array_equal(want[2], plan.indices) and np.array_equal(want[3], plan.indptr)
+        assert np.array_equal(out[s], want[4])
+    assert np.array_equal(out, Axb)
+    # a block shared by the whole batch (ld = 0)
+    out2 = plan.assemble(torch.as_tensor(vals[0]).cuda(), torch.as_tensor(vals[1][3]).cuda(), torch.as_tensor(vals[2]).cuda(),
+                         torch.as_tensor(vals[3]).cuda()).cpu().numpy()
+    want2 = Axb.copy()
+    col = np.repeat(np.arange(n), np.diff(Ap))
+    is12 = (col >= blocks[0].n) & (Ai < blocks[0].m)    # positions of block 12 in the stacked order
+    want2[:, is12] = Axb[3][is12]
+    assert np.array_equal(out2, want2)
+
+
+def test_assemble_refactor_solve_pipeline():
+    """Blocks on the device -> Stack4Plan.assemble -> LuSymbolic.refactor_solve, nothing leaves the GPU in between;
+    x equals the oracle's solution of the assembled systems bit for bit."""
+    import torch
+    from csparse3_b200.assemble import Stack4Plan
+    g = synth.GridCase(118)
+    (n, Ap, Ai, Ax0, Axb, bb), blocks, vals = _jacobian_blocks(g, 19)
+    plan = Stack4Plan(*blocks)
+    sym = LuSymbolic(plan.n, plan.indptr, plan.indices, plan.assemble(*[torch.as_tensor(v[:1]).cuda() for v in vals]).cpu().numpy()[0])
+    Ax_dev = plan.assemble(*[torch.as_tensor(v).cuda() for v in vals])
+    x, st = sym.refactor_solve(Ax_dev, torch.as_tensor(bb).cuda())
+    oLx, oUx, ox = _oracle_batch(sym, n, Ap, Ai, Axb, bb)
+    assert (st.cpu().numpy() == 0).all() and np.array_equal(x.cpu().numpy(), ox)

@@ -3,30 +3,9 @@ import numpy as np
 import scipy.sparse as sp
 
 from conftest import SIX_BY_THREE
-from csparse3_b200 import CscMat, Diag, Diags, pack_4_by_4, scipy_to_mat
+from csparse3_b200 import CscMat, Diag, Diags, scipy_to_mat
 from csparse3_b200 import csc_b200 as B
 from csparse3_b200 import synth
-
-
-def test_stack_matches_reference_fixture(golden_ref):
-    d = golden_ref
-    args = []
-    for c in "abcd":
-        sh = d["st_" + c + "shape"]
-        args += [int(sh[0]), int(sh[1]), d["st_" + c + "i"], d["st_" + c + "p"], d["st_" + c + "x"]]
-    mm, nn, Pi, Pp, Px = B.csc_stack_4_by_4_ff(*args)
-    assert (mm, nn) == tuple(d["ref_st_shape"])
-    assert np.array_equal(Pi, d["ref_st_i"]) and np.array_equal(Pp, d["ref_st_p"]) and np.array_equal(Px, d["ref_st_x"])
-
-
-def test_pack_4_by_4_vs_scipy():
-    """src/test/test_matrix_stacking.py:12-40 at a small seeded size."""
-    k = 15
-    Q = [sp.csc_matrix(sp.random(*s, density=0.2, random_state=t)) for t, s in
-         enumerate([(k, 4 * k), (k, k), (6 * k, 4 * k), (6 * k, k)])]
-    E = sp.hstack((sp.vstack((Q[0], Q[2])), sp.vstack((Q[1], Q[3]))))
-    E1 = pack_4_by_4(*[scipy_to_mat(M) for M in Q])
-    assert (E.toarray() == E1.todense()).all()
 
 
 def test_dense_diag_slices_islands():

@@ -8,6 +8,7 @@ peak, next to the CPU oracle timed on one host thread in the same run; checks th
   * single SpMV on config 1 (2-D Laplacian n = 1e4) and, with --big, config 5 (3-D Laplacian n = 1e6)
                                                                                  12*nnz + 4*(n+1) + 8*n + 8*m bytes
   * SpGEMM A*A and transposition on the same matrices (host-buffer C-ABI calls: copies included)
+  * batched Jacobian assembly [[A11, A12], [A21, A22]] on the config-3 pattern (Stack4Plan)   16*nnz bytes / system
 """
 import argparse
 import json
@@ -69,6 +70,35 @@ def main():
     cpu_ms = (time.perf_counter() - t0) * 1e3 / 256
     bytes_ = plan.bytes_per_system(True) * batch
     out.append({"op": "spmv_batched c3 pattern x10000", "ms": ms, "GBps": bytes_ / ms / 1e6, "frac": bytes_ / ms / 1e6 / P,
+                "bit_exact": ok, "cpu_ms_per_system_1thread": cpu_ms, "gpu_ms_per_system": ms / batch})
+
+    # ---- batched Jacobian assembly [[A11, A12], [A21, A22]] on the config-3 pattern -----------------------------
+    import scipy.sparse as sp
+    from csparse3_b200 import CscMat
+    from csparse3_b200.assemble import Stack4Plan
+    n = g.n
+    J = sp.csc_matrix((np.arange(1, len(g.Ai) + 1, dtype=np.float64), g.Ai, g.Ap), shape=(n, n))
+    n1 = n // 2
+    blocks, vals = [], []
+    for rs, cs in ((slice(0, n1), slice(0, n1)), (slice(0, n1), slice(n1, n)), (slice(n1, n), slice(0, n1)), (slice(n1, n), slice(n1, n))):
+        S = sp.csc_matrix(J[rs, cs]); S.sort_indices()
+        src = S.data.astype(np.int64) - 1
+        blocks.append(CscMat(S.shape[0], S.shape[1], indptr=S.indptr.astype(np.int32), indices=S.indices.astype(np.int32), data=Ax[0][src].copy()))
+        vals.append(np.ascontiguousarray(Ax[:, src]))
+    sp4 = Stack4Plan(*blocks)
+    dv = [torch.as_tensor(np.tile(v, (reps, 1))[:batch]).cuda() for v in vals]
+    dout = torch.empty((batch, sp4.nnz), dtype=torch.float64, device="cuda")
+    ms = timed(lambda: sp4.assemble(*dv, out=dout))
+    ok = bool(np.array_equal(dout[:256].cpu().numpy(), Ax))
+    t0 = time.perf_counter()
+    for k in range(64):
+        a = []
+        for M, v in zip(blocks, vals):
+            a += [M.m, M.n, M.indices, M.indptr, v[k]]
+        orc.csc_stack_4_by_4_ff(*a)
+    cpu_ms = (time.perf_counter() - t0) * 1e3 / 64
+    bytes_ = sp4.bytes_per_system() * batch
+    out.append({"op": "stack4 (Jacobian assembly) c3 pattern x10000", "ms": ms, "GBps": bytes_ / ms / 1e6, "frac": bytes_ / ms / 1e6 / P,
                 "bit_exact": ok, "cpu_ms_per_system_1thread": cpu_ms, "gpu_ms_per_system": ms / batch})
 
     # ---- single-matrix SpMV / SpGEMM / transpose --------------------------------------------------------------
