@@ -118,6 +118,7 @@ struct WideProgram {
     i32 records = 0, immediate_fetches = 0, ngroups = 0;
     i64 near_fma = 0, far_fma = 0;         // update operations whose source column is cached / fetched
     i64 chunks = 0, chunk_ops = 0;         // chunk records and the update operations they hold
+    i64 bank_clashes = 0;                  // shared-memory wavefront collisions left after the slot assignment (model)
 };
 struct Factor;
 struct Schedule;

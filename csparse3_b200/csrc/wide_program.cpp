@@ -562,11 +562,83 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
                 B.i32v(fsrc16); B.u16v(fdst16); B.u16v(funits);
                 B.u16v(R.immediate ? 1 : 0); B.u16v(0); B.i32v(0);
                 // Slot assignment.  Lane group e executes entries e and e + groups with ONE multiplier load, so both come
-                // from the same pair.  Entries 2q and 2q+1 of either half are served by the same shared-memory wavefront:
-                // the operations of a pair are handed out by target parity (lane group 2q gets even targets, 2q+1 odd
-                // ones) whenever possible, so the accumulator accesses are conflict-free.
+                // from the same pair.  Entries 2q and 2q+1 of either half are served by the same shared-memory wavefront
+                // (two 64-byte entries per 128-byte wavefront for 8-system bundles): they collide when they are different
+                // entries of the same parity.
                 std::vector<i32> slot_op((size_t)cap, -1);
-                {
+                auto op_off = [&](i32 x, int which) -> i64 {                   // byte offset of an operand: 0 source, 1 multiplier, 2 target
+                    const Op &o = R.ops[(size_t)x];
+                    const PairDesc &pd = S.pairs[o.pair];
+                    if (which == 0) return (i64)((lsrc0 + pair_src[o.pair] + o.t) * entry);
+                    if (which == 1) return (i64)((size_t)(o.base + pd.moff) * entry);
+                    return (i64)((size_t)(o.base + S.upd_map[(size_t)pd.mapstart + o.t]) * entry);
+                };
+                for (const Op &o : R.ops)
+                    if (pair_src[o.pair] < 0) { *why = "wide refactor: internal error (unresolved source)"; return false; }
+                if (entry == 64 && groups == 8) {
+                    // Units of two operations of one pair, then the perfect matching of the 8 units into wavefront
+                    // partners (and which operation of a unit goes to which half) with the fewest collisions over the
+                    // source loads, the multiplier load and the accumulator load + store: 105 matchings, exhaustive.
+                    struct Unit2 { i32 a, b; };
+                    std::vector<Unit2> un;
+                    for (size_t o = 0; o < R.ops.size();) {
+                        const bool two = o + 1 < R.ops.size() && R.ops[o + 1].pair == R.ops[o].pair;
+                        un.push_back({(i32)o, two ? (i32)o + 1 : -1});
+                        o += two ? 2 : 1;
+                    }
+                    if ((i32)un.size() > groups) { *why = "wide refactor: internal error (lane groups)"; return false; }
+                    while ((i32)un.size() < groups) un.push_back({-1, -1});
+                    auto clash = [&](i32 x, i32 y, int which) -> int {
+                        if (x < 0 || y < 0) return 0;
+                        const i64 p = op_off(x, which), q = op_off(y, which);
+                        return (p != q && ((p >> 6) & 1) == ((q >> 6) & 1)) ? 1 : 0;
+                    };
+                    int cost[8][8], swp[8][8];
+                    for (int u = 0; u < 8; ++u)
+                        for (int v = u + 1; v < 8; ++v) {
+                            int best = 1 << 20, bs = 0;
+                            for (int sw = 0; sw < 2; ++sw) {
+                                if (sw && un[(size_t)v].b < 0) continue;       // entry a of a lane group must be its valid one
+                                const i32 va = sw ? un[(size_t)v].b : un[(size_t)v].a, vb = sw ? un[(size_t)v].a : un[(size_t)v].b;
+                                const int c = clash(un[(size_t)u].a, va, 1) + clash(un[(size_t)u].a, va, 0) + 2 * clash(un[(size_t)u].a, va, 2) +
+                                              clash(un[(size_t)u].b, vb, 0) + 2 * clash(un[(size_t)u].b, vb, 2);
+                                if (c < best) { best = c; bs = sw; }
+                            }
+                            cost[u][v] = best; swp[u][v] = bs;
+                        }
+                    int best_total = 1 << 20, best_mate[8], mate[8];
+                    for (int i = 0; i < 8; ++i) mate[i] = best_mate[i] = -1;
+                    struct Rec2 {
+                        static void go(int total, int (&cost)[8][8], int (&mate)[8], int &best_total, int (&best_mate)[8]) {
+                            int i = 0;
+                            while (i < 8 && mate[i] >= 0) ++i;
+                            if (i == 8) { if (total < best_total) { best_total = total; for (int k = 0; k < 8; ++k) best_mate[k] = mate[k]; } return; }
+                            if (total >= best_total) return;
+                            for (int j = i + 1; j < 8; ++j) {
+                                if (mate[j] >= 0) continue;
+                                mate[i] = j; mate[j] = i;
+                                go(total + cost[i][j], cost, mate, best_total, best_mate);
+                                mate[i] = mate[j] = -1;
+                            }
+                        }
+                    };
+                    Rec2::go(0, cost, mate, best_total, best_mate);
+                    i32 lg = 0;
+                    for (int u = 0; u < 8; ++u) {
+                        const int v = best_mate[u];
+                        if (v < u) continue;
+                        const bool sw = swp[u][v] != 0;
+                        slot_op[(size_t)lg] = un[(size_t)u].a; slot_op[(size_t)(lg + groups)] = un[(size_t)u].b;
+                        slot_op[(size_t)(lg + 1)] = sw ? un[(size_t)v].b : un[(size_t)v].a;
+                        slot_op[(size_t)(lg + 1 + groups)] = sw ? un[(size_t)v].a : un[(size_t)v].b;
+                        // an empty lane group next to a used one: keep its valid entry (if any) in half a
+                        if (slot_op[(size_t)lg] < 0 && slot_op[(size_t)(lg + groups)] >= 0) std::swap(slot_op[(size_t)lg], slot_op[(size_t)(lg + groups)]);
+                        W.bank_clashes += cost[u][v];
+                        lg += 2;
+                    }
+                } else {
+                    // other bundle widths: the operations of a pair are handed out by target parity (lane group 2q gets
+                    // even targets, 2q+1 odd ones) whenever possible
                     const size_t half = entry >= 128 ? 0 : 128 / entry;
                     i32 lg = 0;
                     size_t o = 0;
@@ -596,15 +668,13 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
                         o = o2;
                     }
                 }
+                // Unused entries are still loaded (the kernel does not predicate): they repeat the addresses of their
+                // wavefront partner (a broadcast, no extra wavefront) and are marked invalid.
                 for (i32 u = 0; u < cap; ++u) {
-                    if (slot_op[(size_t)u] >= 0) {
-                        const Op &o = R.ops[(size_t)slot_op[(size_t)u]];
-                        const PairDesc &pd = S.pairs[o.pair];
-                        if (pair_src[o.pair] < 0) { *why = "wide refactor: internal error (unresolved source)"; return false; }
-                        B.u16v((i64)((lsrc0 + pair_src[o.pair] + o.t) * entry));
-                        B.u16v((i64)((size_t)(o.base + pd.moff) * entry));
-                        B.u16v((i64)((size_t)(o.base + S.upd_map[(size_t)pd.mapstart + o.t]) * entry));
-                        B.u16v(1);
+                    const i32 x = slot_op[(size_t)u] >= 0 ? slot_op[(size_t)u] : slot_op[(size_t)(u ^ 1)];
+                    if (x >= 0) {
+                        B.u16v(op_off(x, 0)); B.u16v(op_off(x, 1)); B.u16v(op_off(x, 2));
+                        B.u16v(slot_op[(size_t)u] >= 0 ? 1 : 0);
                     } else {
                         B.u16v((i64)(lsrc0 * entry)); B.u16v(0); B.u16v(0); B.u16v(0);
                     }
@@ -671,9 +741,9 @@ bool compile_wide_refactor(const Schedule &S, const Factor &F, i32 width, i32 gr
         if (getenv("CSP3_DEBUG")) {
             i64 fins = 0;
             for (const Group &g : G) fins += g.fin_cnt;
-            fprintf(stderr, "csp3: wide refactor: %d columns in %d groups, %lld chunk records (%.1f ops each), %lld finalisation records, %d records, stage %zu, %s packer, %d immediate fetches\n",
+            fprintf(stderr, "csp3: wide refactor: %d columns in %d groups, %lld chunk records (%.1f ops each), %lld finalisation records, %d records, stage %zu, %s packer, %d immediate fetches, %.2f modelled bank clashes per chunk\n",
                     n, ngroups, (long long)W.chunks, W.chunks ? (double)W.chunk_ops / (double)W.chunks : 0.0, (long long)fins, nrec, stage,
-                    listsched ? "list" : "in-order", W.immediate_fetches);
+                    listsched ? "list" : "in-order", W.immediate_fetches, W.chunks ? (double)W.bank_clashes / (double)W.chunks : 0.0);
         }
         W.ok = true;
         return true;
