@@ -62,7 +62,8 @@ constexpr int kSvHeader = 24;
 //   lsrc[0, ring_entries)        compile-time managed cache of recently finalised L columns (sequential
 //                                allocation, a column is never split by the wrap)
 //   lsrc[ring_entries, +stage)   landing area of far (not cached) source columns, fetched from the bundle's L
-//                                array with cp.async kWideLookahead records before the pair that consumes them
+//                                array with cp.async kWideLookahead (or up to 3 more) records before the pair that
+//                                consumes them
 // Every record issues at most one fetch and commits exactly one cp.async group, so "wait_group kWideLookahead"
 // at record r guarantees everything requested at records <= r - kWideLookahead has landed (this also covers the
 // program ring itself, whose stage loads ride in the groups of the records that trigger them).
@@ -102,11 +103,17 @@ constexpr int kSvHeader = 24;
 //        cache_off != 0xffff: the L entry is also kept in the L cache (byte offset in the value area)
 // Chunk record (16-byte header + C entries of 8 bytes, C = 2 * lane groups): up to C update operations
 //   acc[tgt] -= lsrc[src] * acc[mult]
-// that are mutually independent (no two share a target, no multiplier is a target of the chunk), taken in order
-// from the column's update sequence (pair after pair in the stored topological order of U(:,k), entry after
-// entry), so executing "all loads, then all stores" per chunk reproduces the sequential result bit for bit.
+// that are mutually independent (no two share a target, no multiplier is a target of the chunk).  Across chunks the
+// operations on one accumulator slot keep the order of the column's update sequence (pair after pair in the stored
+// topological order of U(:,k)) and a pair starts only after the last operation that targets its multiplier, so
+// executing "all loads, then all stores" per chunk reproduces the sequential result bit for bit; inside these two
+// rules the compiler's list scheduler is free (wide_program.cpp).
 // Lane group e of the kernel executes entries e and e + C/2 with ONE multiplier load: when both are valid they have
-// the same mult_off (they belong to the same source column).
+// the same mult_off (they belong to the same source column) and entry e is the valid one when only one is.  An
+// unused entry repeats the offsets of its wavefront partner (entry e ^ 1) with valid == 0: the kernel loads it
+// anyway, as a broadcast.
+// A fetch covers the strict L parts of one or several ADJACENT columns of the bundle's L array (the unit-diagonal
+// positions between them are read and never used).
 //   +0   i32 fetch_src16  +4 u16 fetch_dst16     +6 u16 fetch_units (0: none)
 //   +8   u16 flags: bit 0 = the fetch of THIS record must land before it is used (immediate),
 //                   bits 1-2 = stages entered, bit 3 = wrap                   +10..15 reserved

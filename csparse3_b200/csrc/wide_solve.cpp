@@ -175,6 +175,41 @@ static bool compile_sweep_window(const Factor &F, bool lower, i32 width, i32 gro
         std::push_heap(busy.begin(), busy.end(), cmp);
     }
     if ((size_t)nslots * entry / 16 > 0xfff0) { *why = "wide sweep: too many live rows for 16-bit slot offsets"; return false; }
+    // ---- order of the updates inside a record ------------------------------------------------------------------------
+    // Update u is executed by lane group u % groups; entries 2q and 2q+1 of either half share a shared-memory
+    // wavefront (two 64-byte slots per 128 bytes for 8-system bundles) and collide when they are different slots of
+    // the same parity.  The order inside a record is free (distinct targets, no multiplier is a target), so partners
+    // are chosen with opposite target parity, from the same column (same multiplier: a broadcast) when possible.
+    if (entry == 64) {
+        for (SRec &R : all) {
+            if (R.upds.size() < 2) continue;
+            std::vector<Upd> ev, od, out_u;
+            std::stable_sort(R.upds.begin(), R.upds.end(), [&](const Upd &a, const Upd &b) { return a.mult_row < b.mult_row; });
+            std::vector<Upd> lev, lod;                        // leftovers of the columns
+            for (size_t o = 0; o < R.upds.size();) {
+                size_t o2 = o;
+                ev.clear(); od.clear();
+                while (o2 < R.upds.size() && R.upds[o2].mult_row == R.upds[o].mult_row) { ((slot[R.upds[o2].tgt_row] & 1) ? od : ev).push_back(R.upds[o2]); ++o2; }
+                const size_t m = std::min(ev.size(), od.size());
+                for (size_t k = 0; k < m; ++k) { out_u.push_back(ev[k]); out_u.push_back(od[k]); }
+                for (size_t k = m; k < ev.size(); ++k) lev.push_back(ev[k]);
+                for (size_t k = m; k < od.size(); ++k) lod.push_back(od[k]);
+                o = o2;
+            }
+            // leftovers: opposite target parity first (prefer partners whose multipliers do not collide either)
+            while (!lev.empty() && !lod.empty()) {
+                const Upd a = lev.back(); lev.pop_back();
+                size_t pick = 0;
+                for (size_t k = 0; k < lod.size(); ++k)
+                    if ((slot[lod[k].mult_row] & 1) != (slot[a.mult_row] & 1)) { pick = k; break; }
+                out_u.push_back(a); out_u.push_back(lod[pick]);
+                lod.erase(lod.begin() + (long)pick);
+            }
+            for (const Upd &u : lev) out_u.push_back(u);
+            for (const Upd &u : lod) out_u.push_back(u);
+            R.upds.swap(out_u);
+        }
+    }
     // ---- geometry ------------------------------------------------------------------------------------------------
     const size_t rec_bytes = (size_t)wide_solve_record_bytes(groups);
     size_t stage = 512;

@@ -96,7 +96,7 @@ def main():
         env = dict(os.environ, CSP3_PATH=path, CSP3_CFG=cfg)
         names = {"S": "CSP3_WS_S", "WIN": "CSP3_RF_WIN", "STAGE": "CSP3_SV_STAGE", "RFS": "CSP3_RF_S", "SVS": "CSP3_SV_S",
                  "WIDE": "CSP3_WIDE", "WS": "CSP3_WIDE_S", "WR": "CSP3_WIDE_R", "WF": "CSP3_WIDE_F", "WB": "CSP3_WIDE_BUDGET", "WL": "CSP3_WIDE_LANE",
-                 "GA": "CSP3_WIDE_GA", "PAIRS": "CSP3_WIDE_PAIRS", "RUN": "CSP3_WIDE_RUN", "SCHED": "CSP3_WIDE_SCHED"}
+                 "GA": "CSP3_WIDE_GA", "PAIRS": "CSP3_WIDE_PAIRS", "RUN": "CSP3_WIDE_RUN", "SCHED": "CSP3_WIDE_SCHED", "ACC": "CSP3_WIDE_ACC"}
         for item in filter(None, kv.split(",")):
             k, v = item.split("=")
             env[names[k]] = v
