@@ -110,6 +110,32 @@ def test_spmv_plan_batched_device():
     assert np.array_equal(y1[5], orc.csc_mat_vec_ff(g.n, g.n, g.Ap, g.Ai, Axb[0], b[5]))
 
 
+def test_spmv_plan_large_batch():
+    """Batches of a few hundred systems (grid.y > 1 row blocks per system on the config-3 pattern): bit-identical to
+    the oracle and to a small-batch launch, with beta != 0 and with one value set shared by the batch."""
+    import torch
+    from csparse3_b200.spmv import SpmvPlan
+    for nbus, batch in ((118, 333), (2000, 300)):
+        g = synth.GridCase(nbus)
+        Axb, b = g.jacobian_batch(0, 16)
+        reps = -(-batch // 16)
+        Axt = np.tile(Axb, (reps, 1))[:batch] * np.linspace(0.5, 1.5, batch)[:, None]
+        bt = np.tile(b, (reps, 1))[:batch] + np.arange(batch)[:, None]
+        plan = SpmvPlan(g.n, g.n, g.Ap, g.Ai)
+        dA, dx = torch.as_tensor(Axt).cuda(), torch.as_tensor(bt).cuda()
+        y = plan.matvec(dA, dx).cpu().numpy()
+        small = plan.matvec(dA[:7].contiguous(), dx[:7].contiguous()).cpu().numpy()
+        assert np.array_equal(y[:7], small)
+        for k in (0, 1, batch // 2, batch - 1):
+            assert np.array_equal(y[k], orc.csc_mat_vec_ff(g.n, g.n, g.Ap, g.Ai, Axt[k], bt[k]))
+        y0 = torch.as_tensor(bt[::-1].copy()).cuda()
+        y2 = plan.matvec(dA, dx, y0.clone(), beta=-0.5).cpu().numpy()
+        ref = plan.matvec(dA[:7].contiguous(), dx[:7].contiguous(), y0[:7].clone(), beta=-0.5).cpu().numpy()
+        assert np.array_equal(y2[:7], ref)
+        y1 = plan.matvec(dA[3].contiguous(), dx).cpu().numpy()                                # shared values
+        assert np.array_equal(y1[batch - 1], orc.csc_mat_vec_ff(g.n, g.n, g.Ap, g.Ai, Axt[3], bt[batch - 1]))
+
+
 # ---- transposition / SpGEMM -----------------------------------------------------------------------------------
 @pytest.mark.parametrize("seed", range(3))
 def test_transpose_tocsr_spgemm_vs_oracle(seed):
@@ -293,6 +319,42 @@ def test_lu_config3_sample_device_api():
     import scipy.sparse.linalg as spla
     xr = spla.splu(sp.csc_matrix((Axb[3], Ai, Ap), shape=(n, n))).solve(bb[3])
     assert np.linalg.norm(ox[3] - xr) <= 1e-9 * np.linalg.norm(xr)
+
+
+def test_lu_config3_full_batch_properties():
+    """BASELINE.json's full size (10,000 systems on the 2,000-bus pattern) through size-independent properties:
+    exact homogeneity (A scaled by a power of two scales x by its inverse, bit for bit), exact linearity in b,
+    batch invariance (a system's bits do not depend on the batch it is solved in), residual <= 1e-10 for every
+    system (batched SpMV on the device), and the oracle on a sample."""
+    import torch
+    from csparse3_b200.spmv import SpmvPlan
+    g = synth.GridCase(2000)
+    n, Ap, Ai, Ax0 = g.base_jacobian()
+    sym = LuSymbolic(n, Ap, Ai, Ax0)
+    nb, reps = 250, 40
+    base, bb = g.jacobian_batch(0, nb)
+    scale = 2.0 ** (np.arange(reps) - reps // 2)                   # 2^-20 .. 2^19, block reps // 2 is unscaled
+    Ax = (base[None, :, :] * scale[:, None, None]).reshape(nb * reps, -1)
+    b = np.tile(bb, (reps, 1))
+    dA, db = torch.as_tensor(Ax).cuda(), torch.as_tensor(b).cuda()
+    x, st = sym.refactor_solve(dA, db)
+    assert int(st.abs().max().item()) == 0
+    xh = x.cpu().numpy()
+    x0 = xh[(reps // 2) * nb:(reps // 2 + 1) * nb]
+    for r in range(reps):
+        assert np.array_equal(xh[r * nb:(r + 1) * nb] * scale[r], x0), r
+    # the oracle on a sample of the unscaled block; the same systems alone in a small batch
+    oLx, oUx, ox = _oracle_batch(sym, n, Ap, Ai, base[:6], bb[:6])
+    assert np.array_equal(x0[:6], ox)
+    xs, _ = sym.refactor_solve(torch.as_tensor(base[:6]).cuda(), torch.as_tensor(bb[:6]).cuda())
+    assert np.array_equal(xs.cpu().numpy(), ox)
+    # linearity in b (exact for a factor of two)
+    x2, _ = sym.refactor_solve(dA, 2.0 * db)
+    assert torch.equal(x2, 2.0 * x)
+    # residual of every system
+    r = SpmvPlan(n, n, Ap, Ai).matvec(dA, x) - db
+    rel = (r.norm(dim=1) / db.norm(dim=1)).max().item()
+    assert rel <= 1e-10, rel
 
 
 def test_lu_config4_outages_and_config1():
