@@ -70,6 +70,44 @@ __global__ void k_scan(int m, i32 *cnt, i32 *ptr)
     if (threadIdx.x == 0) ptr[m] = carry;
 }
 
+// same scan on 64-bit values, in place: v[0..m) -> exclusive prefix sums, v[m] = total
+__global__ void k_scan64(int m, i64 *v)
+{
+    __shared__ i64 warp_sum[32];
+    __shared__ i64 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int base = 0; base < m; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const i64 x = (i < m) ? v[i] : 0;
+        i64 s = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const i64 t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        if (lane == 31) warp_sum[warp] = s;
+        __syncthreads();
+        if (warp == 0) {
+            i64 ws = (lane < nw) ? warp_sum[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const i64 t = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += t;
+            }
+            warp_sum[lane] = ws;
+        }
+        __syncthreads();
+        const i64 excl = carry + (warp ? warp_sum[warp - 1] : 0) + s - x;
+        if (i < m) v[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) v[m] = carry;
+}
+
 __global__ void k_bucket_fill(int nnz, const i32 *__restrict__ Ai, i32 *cursor, i32 *bucket)
 {
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += gridDim.x * blockDim.x)
@@ -167,7 +205,7 @@ __device__ __forceinline__ int hash_insert(i32 *keys, unsigned mask, int row, bo
 }
 
 constexpr int kSmallSlots = 1024;     // per-warp table for columns with <= 512 candidate products
-constexpr int kSmallWarps = 4;
+constexpr int kSmallWarps = 3;
 
 // Process one output column with `nthr` cooperating threads (a warp with a shared-memory table, or a whole
 // CTA with a global-memory table).  Products are visited pb-sequentially and pa-parallel, so inside a step
@@ -177,22 +215,66 @@ template <bool NUMERIC, bool BLOCK>
 __device__ void spgemm_column(int j, int tid, int nthr, const i32 *__restrict__ Ap, const i32 *__restrict__ Ai,
                               const double *__restrict__ Ax, const i32 *__restrict__ Bp,
                               const i32 *__restrict__ Bi, const double *__restrict__ Bx, i32 *keys, double *vals,
-                              unsigned mask, i32 *count_out, const i32 *__restrict__ Cp, i32 *Ci, double *Cx)
+                              unsigned mask, i32 *count_out, const i32 *__restrict__ Cp, i32 *Ci, double *Cx,
+                              i32 *compact = nullptr)
 {
     const int slots = (int)mask + 1;
     for (int s = tid; s < slots; s += nthr) { keys[s] = -1; if (NUMERIC) vals[s] = 0.0; }
     if (BLOCK) __syncthreads(); else __syncwarp();
     int fresh_cnt = 0;
-    for (int pb = __ldg(Bp + j); pb < __ldg(Bp + j + 1); ++pb) {
-        const int k = __ldg(Bi + pb);
-        const double bv = NUMERIC ? __ldg(Bx + pb) : 0.0;
-        for (int pa = __ldg(Ap + k) + tid; pa < __ldg(Ap + k + 1); pa += nthr) {
-            bool fresh;
-            const int slot = hash_insert(keys, mask, __ldg(Ai + pa), &fresh);
-            fresh_cnt += fresh;
-            if (NUMERIC) atomicAdd(vals + slot, __dmul_rn(bv, __ldg(Ax + pa)));
+    if (!BLOCK) {
+        // Warp mode.  A step (one entry of B(:,j), i.e. one column of A) depends on three levels of global loads
+        // (Bi -> Ap -> Ai / Ax); walked naively that is ~2,000 cycles of latency per step.  The lanes fetch the B
+        // entries and the A column ranges of up to 32 steps at once, and the first 32 entries of the next step's A
+        // column are loaded before the current step is accumulated.  The order of the sums is unchanged (steps
+        // stay sequential).
+        const int pb0 = __ldg(Bp + j), pb1 = __ldg(Bp + j + 1);
+        for (int base = pb0; base < pb1; base += 32) {
+            int a0_l = 0, a1_l = 0;
+            double bv_l = 0.0;
+            if (base + tid < pb1) {
+                const int k = __ldg(Bi + base + tid);
+                if (NUMERIC) bv_l = __ldg(Bx + base + tid);
+                a0_l = __ldg(Ap + k); a1_l = __ldg(Ap + k + 1);
+            }
+            const int cnt = min(32, pb1 - base);
+            int a0 = __shfl_sync(0xffffffffu, a0_l, 0), a1 = __shfl_sync(0xffffffffu, a1_l, 0);
+            double bv = __shfl_sync(0xffffffffu, bv_l, 0);
+            int row_n = -1;
+            double av_n = 0.0;
+            if (a0 + tid < a1) { row_n = __ldg(Ai + a0 + tid); if (NUMERIC) av_n = __ldg(Ax + a0 + tid); }
+            for (int q = 0; q < cnt; ++q) {
+                const int ca0 = a0, ca1 = a1;
+                const double cbv = bv;
+                int row = row_n;
+                double av = av_n;
+                if (q + 1 < cnt) {
+                    a0 = __shfl_sync(0xffffffffu, a0_l, q + 1); a1 = __shfl_sync(0xffffffffu, a1_l, q + 1);
+                    bv = __shfl_sync(0xffffffffu, bv_l, q + 1);
+                    if (a0 + tid < a1) { row_n = __ldg(Ai + a0 + tid); if (NUMERIC) av_n = __ldg(Ax + a0 + tid); }
+                }
+                for (int pa = ca0 + tid; pa < ca1; pa += 32) {
+                    if (pa >= ca0 + 32) { row = __ldg(Ai + pa); if (NUMERIC) av = __ldg(Ax + pa); }
+                    bool fresh;
+                    const int slot = hash_insert(keys, mask, row, &fresh);
+                    fresh_cnt += fresh;
+                    if (NUMERIC) atomicAdd(vals + slot, __dmul_rn(cbv, av));
+                }
+                __syncwarp();
+            }
         }
-        if (BLOCK) __syncthreads(); else __syncwarp();
+    } else {
+        for (int pb = __ldg(Bp + j); pb < __ldg(Bp + j + 1); ++pb) {
+            const int k = __ldg(Bi + pb);
+            const double bv = NUMERIC ? __ldg(Bx + pb) : 0.0;
+            for (int pa = __ldg(Ap + k) + tid; pa < __ldg(Ap + k + 1); pa += nthr) {
+                bool fresh;
+                const int slot = hash_insert(keys, mask, __ldg(Ai + pa), &fresh);
+                fresh_cnt += fresh;
+                if (NUMERIC) atomicAdd(vals + slot, __dmul_rn(bv, __ldg(Ax + pa)));
+            }
+            __syncthreads();
+        }
     }
     if (!NUMERIC) {
         if (fresh_cnt) atomicAdd(count_out + j, fresh_cnt);
@@ -200,6 +282,28 @@ __device__ void spgemm_column(int j, int tid, int nthr, const i32 *__restrict__ 
     }
     // emit sorted by row: rank of each occupied slot among the occupied slots
     const int base = __ldg(Cp + j);
+    if (!BLOCK && compact != nullptr) {
+        // warp mode: the occupied keys are compacted first (at most slots / 2 of them), so ranking costs
+        // occupied x occupied comparisons instead of occupied x slots
+        int occ = 0;
+        for (int s0 = 0; s0 < slots; s0 += 32) {
+            const int row = keys[s0 + tid];
+            const unsigned bal = __ballot_sync(0xffffffffu, row >= 0);
+            if (row >= 0) compact[occ + __popc(bal & ((1u << tid) - 1u))] = row;
+            occ += __popc(bal);
+        }
+        __syncwarp();
+        for (int s = tid; s < slots; s += nthr) {
+            const int row = keys[s];
+            if (row < 0) continue;
+            int rank = 0;
+            for (int u = 0; u < occ; ++u) rank += (compact[u] < row);
+            Ci[base + rank] = row;
+            Cx[base + rank] = vals[s];
+        }
+        __syncwarp();
+        return;
+    }
     for (int s = tid; s < slots; s += nthr) {
         const int row = keys[s];
         if (row < 0) continue;
@@ -211,37 +315,70 @@ __device__ void spgemm_column(int j, int tid, int nthr, const i32 *__restrict__ 
     if (BLOCK) __syncthreads(); else __syncwarp();
 }
 
-template <bool NUMERIC>
-__global__ void __launch_bounds__(kSmallWarps * 32)
-k_spgemm_small(int ncols, const i32 *__restrict__ list, const i32 *__restrict__ Ap, const i32 *__restrict__ Ai,
-               const double *__restrict__ Ax, const i32 *__restrict__ Bp, const i32 *__restrict__ Bi,
-               const double *__restrict__ Bx, const i32 *__restrict__ slots_of, i32 *count_out,
-               const i32 *__restrict__ Cp, i32 *Ci, double *Cx)
+// hash-table slots of output column j: 0 = empty column, <= kSmallSlots = a warp with a shared-memory table,
+// more = a CTA with a table in global memory.  ub = candidate products of the column (k_spgemm_ub)
+__device__ __forceinline__ i64 spgemm_slots(i32 ub, i64 Am)
 {
-    __shared__ i32 s_keys[kSmallWarps][kSmallSlots];
-    __shared__ double s_vals[NUMERIC ? kSmallWarps : 1][NUMERIC ? kSmallSlots : 1];
+    const i64 cand = min((i64)ub, Am);
+    if (cand == 0) return 0;
+    i64 slots = 32;
+    while (slots < 2 * cand) slots <<= 1;
+    return slots;
+}
+
+// table offsets of the big columns: off[j] = slots (big) or 0, then k_scan64
+__global__ void k_spgemm_bigslots(int Bn, i64 Am, const i32 *__restrict__ ub, i64 *off)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < Bn; j += gridDim.x * blockDim.x) {
+        const i64 slots = spgemm_slots(__ldg(ub + j), Am);
+        off[j] = slots > kSmallSlots ? slots : 0;
+    }
+}
+
+__global__ void k_widen(int n, const i32 *__restrict__ in, i64 *out)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) out[j] = in[j];
+}
+__global__ void k_narrow(int n, const i64 *__restrict__ in, i32 *out)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) out[j] = (i32)min(in[j], (i64)INT32_MAX);
+}
+
+// Warp-per-column kernel for the columns whose table has (LO, SLOTS] slots; WARPS warps per CTA, each with its own
+// table in shared memory.  Two instances are launched: tiny tables (<= 128 slots: 8 warps per CTA, the whole SM full
+// of warps -- the kernel is bound by the latency of its dependent loads) and tables up to kSmallSlots.
+template <bool NUMERIC, int LO, int SLOTS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_spgemm_small_all(int Bn, i64 Am, const i32 *__restrict__ ub, const i32 *__restrict__ Ap, const i32 *__restrict__ Ai,
+                   const double *__restrict__ Ax, const i32 *__restrict__ Bp, const i32 *__restrict__ Bi,
+                   const double *__restrict__ Bx, i32 *count_out, const i32 *__restrict__ Cp, i32 *Ci, double *Cx)
+{
+    __shared__ i32 s_keys[WARPS][SLOTS];
+    __shared__ double s_vals[NUMERIC ? WARPS : 1][NUMERIC ? SLOTS : 1];
+    __shared__ i32 s_compact[NUMERIC ? WARPS : 1][NUMERIC ? SLOTS / 2 : 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int c = blockIdx.x * kSmallWarps + warp; c < ncols; c += gridDim.x * kSmallWarps) {
-        const int j = __ldg(list + c);
-        const unsigned mask = (unsigned)__ldg(slots_of + c) - 1u;
+    for (int j = blockIdx.x * WARPS + warp; j < Bn; j += gridDim.x * WARPS) {
+        const i64 slots = spgemm_slots(__ldg(ub + j), Am);
+        if (slots <= LO || slots > SLOTS) continue;
         spgemm_column<NUMERIC, false>(j, lane, 32, Ap, Ai, Ax, Bp, Bi, Bx, s_keys[warp],
-                                      NUMERIC ? (double *)s_vals[warp] : (double *)nullptr, mask, count_out, Cp, Ci, Cx);
+                                      NUMERIC ? (double *)s_vals[warp] : (double *)nullptr, (unsigned)slots - 1u, count_out, Cp, Ci, Cx,
+                                      NUMERIC ? (i32 *)s_compact[warp] : (i32 *)nullptr);
     }
 }
 
 template <bool NUMERIC>
 __global__ void __launch_bounds__(kThreads)
-k_spgemm_big(int ncols, const i32 *__restrict__ list, const i32 *__restrict__ Ap, const i32 *__restrict__ Ai,
-             const double *__restrict__ Ax, const i32 *__restrict__ Bp, const i32 *__restrict__ Bi,
-             const double *__restrict__ Bx, const i32 *__restrict__ slots_of, const i64 *__restrict__ tab_off,
-             i32 *tab_keys, double *tab_vals, i32 *count_out, const i32 *__restrict__ Cp, i32 *Ci, double *Cx)
+k_spgemm_big_all(int Bn, i64 Am, const i32 *__restrict__ ub, const i64 *__restrict__ tab_off, const i32 *__restrict__ Ap,
+                 const i32 *__restrict__ Ai, const double *__restrict__ Ax, const i32 *__restrict__ Bp, const i32 *__restrict__ Bi,
+                 const double *__restrict__ Bx, i32 *tab_keys, double *tab_vals, i32 *count_out, const i32 *__restrict__ Cp,
+                 i32 *Ci, double *Cx)
 {
-    for (int c = blockIdx.x; c < ncols; c += gridDim.x) {
-        const int j = __ldg(list + c);
-        const unsigned mask = (unsigned)__ldg(slots_of + c) - 1u;
-        const i64 off = tab_off[c];
+    for (int j = blockIdx.x; j < Bn; j += gridDim.x) {
+        const i64 slots = spgemm_slots(__ldg(ub + j), Am);                  // uniform over the CTA
+        if (slots <= kSmallSlots) continue;
+        const i64 off = tab_off[j];
         spgemm_column<NUMERIC, true>(j, threadIdx.x, blockDim.x, Ap, Ai, Ax, Bp, Bi, Bx, tab_keys + off,
-                                     NUMERIC ? tab_vals + off : nullptr, mask, count_out, Cp, Ci, Cx);
+                                     NUMERIC ? tab_vals + off : nullptr, (unsigned)slots - 1u, count_out, Cp, Ci, Cx);
     }
 }
 
@@ -356,63 +493,54 @@ int spgemm_device(bool numeric, i64 Am, i64 An, const i32 *Ap, const i32 *Ai, co
 {
     if (An != Bm) { set_error("spgemm: inner dimensions differ (%lld vs %lld)", (long long)An, (long long)Bm); return -1; }
     if (Bn == 0) { if (!numeric) { CSP3_CUDA(cudaMemsetAsync(Cp, 0, 4, st)); if (nnz_out) *nnz_out = 0; } return 0; }
-    DevBuf ub(st);
-    if (ub.alloc((size_t)Bn * 4)) { set_error("device alloc failed"); return -3; }
+    // Planning stays on the device (one 8-byte read-back for the size of the global hash tables): candidate
+    // products per column -> table size per column -> offsets of the big columns' tables by a prefix sum.
+    DevBuf ub(st), boff(st), tkeys(st), tvals(st), cnt(st);
+    if (ub.alloc((size_t)Bn * 4) || boff.alloc((size_t)(Bn + 1) * 8)) { set_error("device alloc failed"); return -3; }
     k_spgemm_ub<<<grid_for(Bn, kThreads), kThreads, 0, st>>>((int)Bn, Ap, Bp, Bi, ub.as<i32>());
-    std::vector<i32> h_ub((size_t)Bn);
-    CSP3_CUDA(cudaMemcpyAsync(h_ub.data(), ub.p, (size_t)Bn * 4, cudaMemcpyDeviceToHost, st));
-    CSP3_CUDA(cudaStreamSynchronize(st));
-    // partition columns by candidate-product count
-    std::vector<i32> small_list, small_slots, big_list, big_slots;
-    std::vector<i64> big_off;
+    k_spgemm_bigslots<<<grid_for(Bn, kThreads), kThreads, 0, st>>>((int)Bn, Am, ub.as<i32>(), boff.as<i64>());
+    k_scan64<<<1, 1024, 0, st>>>((int)Bn, boff.as<i64>());
     i64 tab_total = 0;
-    for (i64 j = 0; j < Bn; ++j) {
-        const i64 cand = std::min<i64>(h_ub[j], Am);
-        if (cand == 0) continue;
-        i64 slots = 32;
-        while (slots < 2 * cand) slots <<= 1;
-        if (slots <= kSmallSlots) { small_list.push_back((i32)j); small_slots.push_back((i32)slots); }
-        else { big_list.push_back((i32)j); big_slots.push_back((i32)slots); big_off.push_back(tab_total); tab_total += slots; }
+    CSP3_CUDA(cudaMemcpyAsync(&tab_total, boff.as<i64>() + Bn, 8, cudaMemcpyDeviceToHost, st));
+    CSP3_CUDA(cudaStreamSynchronize(st));
+    if (tab_total > 0 && (tkeys.alloc((size_t)tab_total * 4) || (numeric && tvals.alloc((size_t)tab_total * 8)))) {
+        set_error("spgemm: device alloc failed");
+        return -3;
     }
-    DevBuf d_small(st), d_small_slots(st), d_big(st), d_big_slots(st), d_big_off(st), tkeys(st), tvals(st), cnt(st);
-    auto upload = [&](DevBuf &d, const void *src, size_t bytes) -> int {
-        if (d.alloc(bytes)) return -3;
-        if (bytes) return cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, st) == cudaSuccess ? 0 : -2;
-        return 0;
-    };
-    if (upload(d_small, small_list.data(), small_list.size() * 4) || upload(d_small_slots, small_slots.data(), small_slots.size() * 4) ||
-        upload(d_big, big_list.data(), big_list.size() * 4) || upload(d_big_slots, big_slots.data(), big_slots.size() * 4) ||
-        upload(d_big_off, big_off.data(), big_off.size() * 8) || tkeys.alloc((size_t)tab_total * 4) ||
-        (numeric && tvals.alloc((size_t)tab_total * 8))) { set_error("spgemm: device alloc/copy failed"); return -3; }
     i32 *count = nullptr;
     if (!numeric) {
         if (cnt.alloc((size_t)(Bn + 1) * 4)) { set_error("device alloc failed"); return -3; }
         CSP3_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)(Bn + 1) * 4, st));
         count = cnt.as<i32>();
     }
-    const int ns = (int)small_list.size(), nb = (int)big_list.size();
-    if (ns) {
-        const int g = grid_for(ns, kSmallWarps, kNumSMs * 8);
-        if (numeric) k_spgemm_small<true><<<g, kSmallWarps * 32, 0, st>>>(ns, d_small.as<i32>(), Ap, Ai, Ax, Bp, Bi, Bx, d_small_slots.as<i32>(), nullptr, Cp, Ci, Cx);
-        else k_spgemm_small<false><<<g, kSmallWarps * 32, 0, st>>>(ns, d_small.as<i32>(), Ap, Ai, Ax, Bp, Bi, Bx, d_small_slots.as<i32>(), count, nullptr, nullptr, nullptr);
+    {
+        constexpr int kTiny = 128, kTinyWarps = 8;
+        const int g1 = grid_for(Bn, kTinyWarps, kNumSMs * 8), g2 = grid_for(Bn, kSmallWarps, kNumSMs * 5);
+        if (numeric) {
+            k_spgemm_small_all<true, 0, kTiny, kTinyWarps><<<g1, kTinyWarps * 32, 0, st>>>((int)Bn, Am, ub.as<i32>(), Ap, Ai, Ax, Bp, Bi, Bx, nullptr, Cp, Ci, Cx);
+            k_spgemm_small_all<true, kTiny, kSmallSlots, kSmallWarps><<<g2, kSmallWarps * 32, 0, st>>>((int)Bn, Am, ub.as<i32>(), Ap, Ai, Ax, Bp, Bi, Bx, nullptr, Cp, Ci, Cx);
+        } else {
+            k_spgemm_small_all<false, 0, kTiny, kTinyWarps><<<g1, kTinyWarps * 32, 0, st>>>((int)Bn, Am, ub.as<i32>(), Ap, Ai, Ax, Bp, Bi, Bx, count, nullptr, nullptr, nullptr);
+            k_spgemm_small_all<false, kTiny, kSmallSlots, kSmallWarps><<<g2, kSmallWarps * 32, 0, st>>>((int)Bn, Am, ub.as<i32>(), Ap, Ai, Ax, Bp, Bi, Bx, count, nullptr, nullptr, nullptr);
+        }
     }
-    if (nb) {
-        const int g = std::min(nb, kNumSMs * 4);
-        if (numeric) k_spgemm_big<true><<<g, kThreads, 0, st>>>(nb, d_big.as<i32>(), Ap, Ai, Ax, Bp, Bi, Bx, d_big_slots.as<i32>(), d_big_off.as<i64>(), tkeys.as<i32>(), tvals.as<double>(), nullptr, Cp, Ci, Cx);
-        else k_spgemm_big<false><<<g, kThreads, 0, st>>>(nb, d_big.as<i32>(), Ap, Ai, Ax, Bp, Bi, Bx, d_big_slots.as<i32>(), d_big_off.as<i64>(), tkeys.as<i32>(), nullptr, count, nullptr, nullptr, nullptr);
+    if (tab_total > 0) {
+        const int g = (int)std::min<i64>(Bn, kNumSMs * 4);
+        if (numeric) k_spgemm_big_all<true><<<g, kThreads, 0, st>>>((int)Bn, Am, ub.as<i32>(), boff.as<i64>(), Ap, Ai, Ax, Bp, Bi, Bx, tkeys.as<i32>(), tvals.as<double>(), nullptr, Cp, Ci, Cx);
+        else k_spgemm_big_all<false><<<g, kThreads, 0, st>>>((int)Bn, Am, ub.as<i32>(), boff.as<i64>(), Ap, Ai, Ax, Bp, Bi, Bx, tkeys.as<i32>(), nullptr, count, nullptr, nullptr, nullptr);
     }
     CSP3_CUDA(cudaGetLastError());
     if (!numeric) {
-        // Cp = exclusive scan of counts; overflow check on the host (sparsetools csr.h:591-596)
-        std::vector<i32> h_cnt((size_t)Bn);
-        CSP3_CUDA(cudaMemcpyAsync(h_cnt.data(), cnt.p, (size_t)Bn * 4, cudaMemcpyDeviceToHost, st));
-        CSP3_CUDA(cudaStreamSynchronize(st));
-        std::vector<i32> h_cp((size_t)Bn + 1);
+        // Cp = exclusive scan of the counts (64-bit on the device; overflow check as sparsetools csr.h:591-596)
+        DevBuf wide(st);
+        if (wide.alloc((size_t)(Bn + 1) * 8)) { set_error("device alloc failed"); return -3; }
+        k_widen<<<grid_for(Bn, kThreads), kThreads, 0, st>>>((int)Bn, cnt.as<i32>(), wide.as<i64>());
+        k_scan64<<<1, 1024, 0, st>>>((int)Bn, wide.as<i64>());
+        k_narrow<<<grid_for(Bn + 1, kThreads), kThreads, 0, st>>>((int)Bn + 1, wide.as<i64>(), Cp);
         i64 run = 0;
-        for (i64 j = 0; j < Bn; ++j) { h_cp[j] = (i32)run; run += h_cnt[j]; if (run > INT32_MAX) { set_error("nnz of the result is too large"); return -4; } }
-        h_cp[Bn] = (i32)run;
-        CSP3_CUDA(cudaMemcpyAsync(Cp, h_cp.data(), (size_t)(Bn + 1) * 4, cudaMemcpyHostToDevice, st));
+        CSP3_CUDA(cudaMemcpyAsync(&run, wide.as<i64>() + Bn, 8, cudaMemcpyDeviceToHost, st));
         CSP3_CUDA(cudaStreamSynchronize(st));
+        if (run > INT32_MAX) { set_error("nnz of the result is too large"); return -4; }
         if (nnz_out) *nnz_out = run;
     }
     return 0;

@@ -127,6 +127,31 @@ def main():
         bytes_ = 12 * (2 * nnz + nnzC) + 4 * (3 * n + 3)
         out.append({"op": "spgemm A*A " + name + " (host call incl. copies)", "ms": gpu_ms, "nnzC": nnzC, "GBps": bytes_ / gpu_ms / 1e6,
                     "Cp_exact": same_p, "values_exact": same_v, "cpu_ms_1thread": cpu_ms})
+        # device-resident SpGEMM (the two-phase C-ABI with device pointers): numeric phase alone and both phases
+        import ctypes as C
+        from csparse3_b200 import _lib
+        L = _lib.lib()
+        dAp, dAi = torch.as_tensor(Ap).cuda(), torch.as_tensor(Ai).cuda()
+        dCp = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+        nz = C.c_int64(0)
+        stream = torch.cuda.current_stream().cuda_stream
+
+        def symbolic():
+            _lib.check(L.csp3_spgemm_symbolic(n, n, dAp.data_ptr(), dAi.data_ptr(), n, n, dAp.data_ptr(), dAi.data_ptr(),
+                                              dCp.data_ptr(), C.byref(nz), stream), "spgemm symbolic")
+        symbolic()
+        dCi = torch.empty(nz.value, dtype=torch.int32, device="cuda")
+        dCx = torch.empty(nz.value, dtype=torch.float64, device="cuda")
+
+        def numeric():
+            _lib.check(L.csp3_spgemm_numeric(n, n, dAp.data_ptr(), dAi.data_ptr(), dAx.data_ptr(), n, n, dAp.data_ptr(), dAi.data_ptr(),
+                                             dAx.data_ptr(), dCp.data_ptr(), dCi.data_ptr(), dCx.data_ptr(), stream), "spgemm numeric")
+        ms_num = timed(numeric)
+        ms_both = timed(lambda: (symbolic(), numeric()))
+        same_dev = bool(np.array_equal(dCp.cpu().numpy(), Cp) and np.array_equal(dCi.cpu().numpy(), Ci) and np.array_equal(dCx.cpu().numpy(), Cx))
+        out.append({"op": "spgemm A*A " + name + " (device resident)", "ms_numeric": ms_num, "ms_symbolic_plus_numeric": ms_both, "nnzC": int(nz.value),
+                    "GBps_numeric": bytes_ / ms_num / 1e6, "frac_numeric": bytes_ / ms_num / 1e6 / P, "GBps_both": bytes_ / ms_both / 1e6,
+                    "equals_host_call": same_dev, "cpu_ms_1thread": cpu_ms})
         t0 = time.perf_counter(); T = B.csc_transpose(n, n, Ap, Ai, Axm); gpu_ms = (time.perf_counter() - t0) * 1e3
         t0 = time.perf_counter(); To = orc.csc_transpose(n, n, Ap, Ai, Axm); cpu_ms = (time.perf_counter() - t0) * 1e3
         out.append({"op": "transpose " + name + " (host call incl. copies)", "ms": gpu_ms,
