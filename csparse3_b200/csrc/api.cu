@@ -55,8 +55,12 @@ int require_device()
 // RAII device buffer for the *_host entry points (synchronous semantics, default stream)
 struct Dev {
     void *p = nullptr;
-    ~Dev() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16) == cudaSuccess ? 0 : -1; }
+    ~Dev() { if (p) cudaFreeAsync(p, nullptr); }
+    int alloc(size_t bytes)
+    {
+        keep_device_pool();
+        return cudaMallocAsync(&p, bytes ? bytes : 16, nullptr) == cudaSuccess ? 0 : -1;
+    }
     int put(const void *src, size_t bytes)
     {
         if (alloc(bytes)) return -1;

@@ -429,11 +429,32 @@ struct DevBuf {
     cudaStream_t st;
     explicit DevBuf(cudaStream_t s) : st(s) {}
     ~DevBuf() { if (p) cudaFreeAsync(p, st); }
-    int alloc(size_t bytes) { return cudaMallocAsync(&p, std::max<size_t>(bytes, 16), st) == cudaSuccess ? 0 : -1; }
+    int alloc(size_t bytes)
+    {
+        keep_device_pool();
+        return cudaMallocAsync(&p, std::max<size_t>(bytes, 16), st) == cudaSuccess ? 0 : -1;
+    }
     template <class T> T *as() { return (T *)p; }
 };
 
 }  // namespace
+
+// The stream-ordered pool hands freed memory back to the driver at every synchronisation by default; the entry
+// points synchronise (they read sizes back), so every call paid for fresh driver allocations (~1 ms).  Keep up to
+// 1 GiB cached per device instead.
+void keep_device_pool()
+{
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t threshold = 1ull << 30;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    cudaGetLastError();
+    done[dev] = true;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 int transpose_device(i64 m, i64 n, const i32 *Ap, const i32 *Ai, const double *Ax, i32 nnz, i32 *Cp, i32 *Ci,

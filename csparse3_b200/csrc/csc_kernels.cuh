@@ -4,6 +4,9 @@
 
 namespace csp3 {
 
+// keeps freed stream-ordered allocations cached in the device's default pool (called by the allocating helpers)
+void keep_device_pool();
+
 struct SpmvPlanData {
     i64 m = 0, n = 0, nnz = 0;
     i32 *rp = nullptr, *rc = nullptr, *perm = nullptr;   // CSR view: row ptr, column, source CSC entry

@@ -152,8 +152,16 @@ def main():
         out.append({"op": "spgemm A*A " + name + " (device resident)", "ms_numeric": ms_num, "ms_symbolic_plus_numeric": ms_both, "nnzC": int(nz.value),
                     "GBps_numeric": bytes_ / ms_num / 1e6, "frac_numeric": bytes_ / ms_num / 1e6 / P, "GBps_both": bytes_ / ms_both / 1e6,
                     "equals_host_call": same_dev, "cpu_ms_1thread": cpu_ms})
+        dTp = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+        dTi = torch.empty(nnz, dtype=torch.int32, device="cuda")
+        dTx = torch.empty(nnz, dtype=torch.float64, device="cuda")
+        ms_t = timed(lambda: _lib.check(L.csp3_csc_transpose(n, n, dAp.data_ptr(), dAi.data_ptr(), dAx.data_ptr(), dTp.data_ptr(),
+                                                            dTi.data_ptr(), dTx.data_ptr(), stream), "transpose"))
+        tbytes = 2 * (12 * nnz + 4 * (n + 1))
         t0 = time.perf_counter(); T = B.csc_transpose(n, n, Ap, Ai, Axm); gpu_ms = (time.perf_counter() - t0) * 1e3
         t0 = time.perf_counter(); To = orc.csc_transpose(n, n, Ap, Ai, Axm); cpu_ms = (time.perf_counter() - t0) * 1e3
+        out.append({"op": "transpose " + name + " (device resident)", "ms": ms_t, "GBps": tbytes / ms_t / 1e6, "frac": tbytes / ms_t / 1e6 / P,
+                    "exact": bool(np.array_equal(dTp.cpu().numpy(), T[2]) and np.array_equal(dTi.cpu().numpy(), T[3]) and np.array_equal(dTx.cpu().numpy(), T[4]))})
         out.append({"op": "transpose " + name + " (host call incl. copies)", "ms": gpu_ms,
                     "exact": bool(all(np.array_equal(u, v) for u, v in zip(T[2:], To[2:]))), "cpu_ms_1thread": cpu_ms})
     for r in out:
