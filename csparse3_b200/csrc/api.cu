@@ -176,6 +176,7 @@ int csp3_spmv_plan_create(int64_t m, int64_t n, const int32_t *Ap_dev, const int
         return CSP3_ERR_ALLOC;
     }
     int rc = transpose_device(m, n, Ap_dev, Ai_dev, nullptr, nnz, P->d.rp, P->d.rc, nullptr, P->d.perm, st);
+    if (rc == 0) rc = spmv_plan_pack(P->d, st);
     if (rc) { csp3_spmv_plan_destroy(P); return rc; }
     *plan = P;
     return 0;
@@ -184,7 +185,7 @@ int csp3_spmv_plan_create(int64_t m, int64_t n, const int32_t *Ap_dev, const int
 int csp3_spmv_plan_destroy(csp3_spmv_plan *plan)
 {
     if (!plan) return 0;
-    cudaFree(plan->d.rp); cudaFree(plan->d.rc); cudaFree(plan->d.perm);
+    cudaFree(plan->d.rp); cudaFree(plan->d.rc); cudaFree(plan->d.perm); cudaFree(plan->d.pk);
     delete plan;
     return 0;
 }

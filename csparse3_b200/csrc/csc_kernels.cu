@@ -160,6 +160,31 @@ __global__ void k_spmv(int m, int n, i64 nnz_stride, const i32 *__restrict__ rp,
     }
 }
 
+// same as k_spmv<1> with one packed index word per entry (patterns with nnz, n < 65536)
+__global__ void k_spmv_packed(int m, int n, i64 nnz_stride, const i32 *__restrict__ rp, const uint32_t *__restrict__ pk,
+                              const double *__restrict__ Ax, const double *__restrict__ x, double *y, double beta)
+{
+    const i64 b = blockIdx.y;
+    const double *Axb = Ax + b * nnz_stride;
+    const double *xb = x + b * n;
+    double *yb = y + b * m;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
+        const int beg = __ldg(rp + r), end = __ldg(rp + r + 1);
+        double s = (beta != 0.0) ? beta * yb[r] : 0.0;
+        for (int t = beg; t < end; ++t) {
+            const uint32_t w = __ldg(pk + t);
+            s = __dadd_rn(s, __dmul_rn(__ldg(Axb + (w & 0xffffu)), __ldg(xb + (w >> 16))));
+        }
+        yb[r] = s;
+    }
+}
+
+__global__ void k_pack_index(i32 nnz, const i32 *__restrict__ perm, const i32 *__restrict__ rc, uint32_t *pk)
+{
+    for (i32 t = blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += gridDim.x * blockDim.x)
+        pk[t] = (uint32_t)perm[t] | ((uint32_t)rc[t] << 16);
+}
+
 // Y[r][v] += sum_t Ax[perm[t]] * X[col[t]][v]   (row-major X, Y; thread per (r, v)), sparsetools csc.h:68-84
 __global__ void k_spmm(int m, int nv, const i32 *__restrict__ rp, const i32 *__restrict__ rc,
                        const i32 *__restrict__ perm, const double *__restrict__ Ax, const double *__restrict__ X,
@@ -474,6 +499,15 @@ int transpose_device(i64 m, i64 n, const i32 *Ap, const i32 *Ai, const double *A
     return 0;
 }
 
+int spmv_plan_pack(SpmvPlanData &P, cudaStream_t st)
+{
+    if (P.pk || P.nnz == 0 || P.nnz >= 65536 || P.n >= 65536) return 0;
+    CSP3_CUDA(cudaMalloc((void **)&P.pk, (size_t)P.nnz * 4));
+    k_pack_index<<<(unsigned)((P.nnz + 255) / 256), 256, 0, st>>>((i32)P.nnz, P.perm, P.rc, P.pk);
+    CSP3_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int spmv_device(const SpmvPlanData &P, i64 batch, const double *Ax, i64 stride_ax, const double *x, double *y,
                 double beta, cudaStream_t st)
 {
@@ -487,7 +521,10 @@ int spmv_device(const SpmvPlanData &P, i64 batch, const double *Ax, i64 stride_a
     for (i64 b0 = 0; b0 < batch; b0 += 65535) {
         const i64 nb = std::min<i64>(65535, batch - b0);
         dim3 grid((unsigned)gx, (unsigned)nb);
-        if (wide)
+        if (!wide && P.pk)
+            k_spmv_packed<<<grid, kThreads, 0, st>>>((int)P.m, (int)P.n, stride_ax, P.rp, P.pk,
+                                                     Ax + b0 * stride_ax, x + b0 * P.n, y + b0 * P.m, beta);
+        else if (wide)
             k_spmv<8><<<grid, kThreads, 0, st>>>((int)P.m, (int)P.n, stride_ax, P.rp, P.rc, P.perm,
                                                  Ax + b0 * stride_ax, x + b0 * P.n, y + b0 * P.m, beta);
         else

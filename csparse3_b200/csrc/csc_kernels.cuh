@@ -10,7 +10,9 @@ void keep_device_pool();
 struct SpmvPlanData {
     i64 m = 0, n = 0, nnz = 0;
     i32 *rp = nullptr, *rc = nullptr, *perm = nullptr;   // CSR view: row ptr, column, source CSC entry
+    uint32_t *pk = nullptr;                              // perm | column << 16 when nnz, n < 65536 (one index load per entry)
 };
+int spmv_plan_pack(SpmvPlanData &P, cudaStream_t st);    // fills pk when the pattern qualifies
 
 // C = A' (== CSC->CSR of A).  Any of Ci, Cx, perm may be nullptr.  perm[t] = source entry of output entry t.
 int transpose_device(i64 m, i64 n, const i32 *Ap, const i32 *Ai, const double *Ax, i32 nnz, i32 *Cp, i32 *Ci,
