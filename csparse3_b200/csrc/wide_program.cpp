@@ -1,7 +1,11 @@
 // wide_program.cpp -- host compiler of the "wide" (lane = system) refactor program executed by lu_wide.cu.
 // Record formats: program.hpp.  No reference counterpart; the arithmetic the program
 // encodes is the frozen-pattern left-looking cs_lu column update of oracle/csp3_oracle.c, operation for
-// operation and, for every column, in the same order.
+// operation and, for every entry of every column, in the same order (which is all that bit-exactness needs: the
+// list scheduler below reorders operations on different entries freely).
+// Knobs (environment, read once): CSP3_WIDE_SCHED=0 in-order chunk packer, CSP3_WIDE_PAIRS source columns a column
+// offers to the scheduler at a time (6), CSP3_WIDE_RUN longest landing run in entries, CSP3_WIDE_GA A entries per
+// group (<= kWideGroupA), CSP3_WIDE_ACC accumulator slots.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
