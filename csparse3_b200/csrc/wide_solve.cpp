@@ -85,6 +85,7 @@ static bool compile_sweep_window(const Factor &F, bool lower, i32 width, i32 gro
     i32 ndone = 0;
     // forward sweep: only columns close to the oldest unfinished one are candidates, otherwise the scheduler runs
     // ahead into far subtrees and the front (live rows) grows several-fold
+    static const bool split_columns = !(getenv("CSP3_SWEEP_SPLIT") && atoi(getenv("CSP3_SWEEP_SPLIT")) == 0);
     const i32 window = lower ? fwd_window : n;
     i32 oldest = 0;                                       // natural position of the oldest unfinished column
     auto natural = [&](i32 j) { return lower ? j : n - 1 - j; };
@@ -93,18 +94,24 @@ static bool compile_sweep_window(const Factor &F, bool lower, i32 width, i32 gro
         while (oldest < n && done[col_at(oldest)]) ++oldest;
         // first ready column that fits the current record entirely
         const i32 rid = (i32)recs.size() - 1;
-        size_t pick = ready.size();
+        size_t pick = ready.size(), spill = ready.size();
         const size_t scan = std::min<size_t>(ready.size(), 96);
         for (size_t c = 0; c < scan && pick == ready.size(); ++c) {
             const i32 j = ready[c].second;
             if (natural(j) > oldest + window) continue;
             if (tgt_stamp[j] == rid || (i32)cur().fins.size() >= E) continue;
-            if ((i32)cur().upds.size() + (col_end(j) - col_begin(j)) > cap_u) continue;
             if (new_rows(j) > credit) continue;
+            // a column whose first update can still go into this record may start here and spill into the next
+            // record(s): its row is finalised now, so the updates it has left are free to follow
+            if (spill == ready.size() && split_columns && (i32)cur().upds.size() + 2 <= cap_u && col_begin(j) < col_end(j) &&
+                tgt_stamp[Gi[col_begin(j)]] != rid)
+                spill = c;
+            if ((i32)cur().upds.size() + (col_end(j) - col_begin(j)) > cap_u) continue;
             bool ok = true;
             for (i32 p = col_begin(j); p < col_end(j) && ok; ++p) ok = tgt_stamp[Gi[p]] != rid;
             if (ok) pick = c;
         }
+        if (pick == ready.size() && spill != ready.size()) pick = spill;
         if (pick == ready.size()) {
             if (!cur().fins.empty() || !cur().upds.empty()) { new_record(); continue; }
             pick = 0;                                     // empty record: take the best column, it may span records
