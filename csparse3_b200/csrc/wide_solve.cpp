@@ -3,6 +3,7 @@
 // oracle/csp3_oracle.c (orc_csc_lsolve, orc_csc_usolve): column after column, every update of a column in
 // storage order, so each entry of the solution sees its subtractions in exactly the sequential order.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -276,13 +277,15 @@ static bool compile_sweep_window(const Factor &F, bool lower, i32 width, i32 gro
 bool compile_wide_sweep(const Factor &F, bool lower, i32 width, i32 groups, size_t smem_budget, WideSweep &W, const char **why)
 {
     if (!lower) return compile_sweep_window(F, lower, width, groups, 0, W, why);
-    const i32 windows[5] = {64, 32, 16, 8, 4};
+    // the widest window whose live rows fit the shared-memory budget
+    const i32 windows[8] = {64, 48, 32, 24, 16, 12, 8, 4};
     bool any = false;
-    for (int t = 0; t < 5; ++t) {
+    for (int t = 0; t < 8; ++t) {
         WideSweep T;
         if (!compile_sweep_window(F, lower, width, groups, windows[t], T, why)) continue;
         any = true;
         W = std::move(T);
+        if (getenv("CSP3_DEBUG")) fprintf(stderr, "csp3: forward sweep window %d: %d records, %d slots, %zu bytes\n", windows[t], W.records, W.nslots, W.smem_bytes);
         if (W.smem_bytes <= smem_budget) break;
     }
     return any;
