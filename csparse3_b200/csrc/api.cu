@@ -9,6 +9,7 @@
 #include "../../include/csparse3_b200.h"
 #include "common.cuh"
 #include "csc_kernels.cuh"
+#include "panel_program.hpp"
 
 namespace csp3 {
 
@@ -34,6 +35,8 @@ Tuning &tuning()
         if (getenv("CSP3_WIDE_SOLVE")) v.wide_solve = env("CSP3_WIDE_SOLVE");
         v.wide_S = env("CSP3_WIDE_S"); v.wide_R = env("CSP3_WIDE_LANE"); v.wide_ring = env("CSP3_WIDE_R"); v.wide_stage = env("CSP3_WIDE_F");
         v.wide_budget = env("CSP3_WIDE_BUDGET");
+        if (getenv("CSP3_PANEL")) v.panel = env("CSP3_PANEL");
+        v.panel_fma = env("CSP3_PANEL_FMA");
         return v;
     }();
     return t;
@@ -93,6 +96,7 @@ struct csp3_lu_symbolic {
     Schedule S;
     WideProgram W;                     // wide refactor program (ok == false: pattern does not fit, v3 kernels are used)
     WideSweep WF, WB;                  // wide forward / backward sweep programs
+    PanelProgram PP;                   // panel refactor program (lu_panel.cu); ok == false: the wide / v3 kernels are used
     std::vector<i32> qinv;             // x[c] = x_pivot_order[qinv[c]]
     DevSchedule dev[kMaxDevices];
     // staging for csp3_lu_refactor_solve_host (per device, lazily created)
@@ -112,6 +116,17 @@ struct csp3_lu_symbolic {
 static void compile_wide(csp3_lu_symbolic &Sy)
 {
     const Tuning &t = tuning();
+    if (Sy.n > 0) {
+        Sy.qinv.assign((size_t)Sy.n, 0);
+        for (i64 i = 0; i < Sy.n; ++i) Sy.qinv[(size_t)(Sy.q.empty() ? i : Sy.q[(size_t)i])] = (i32)i;
+    }
+    if (t.panel != 0 && Sy.n > 0) {
+        const char *why = "";
+        if (!compile_panel_refactor(Sy.n, Sy.Ap.data(), Sy.Ai.data(), Sy.q, Sy.F, 8, 4, Sy.PP, &why)) {
+            if (getenv("CSP3_DEBUG")) fprintf(stderr, "csp3: panel refactor unavailable: %s\n", why);
+            Sy.PP = PanelProgram();
+        }
+    }
     if (t.wide == 0 || Sy.n == 0) return;
     const i32 width = (t.wide_S == 4 || t.wide_S == 16 || t.wide_S == 32) ? t.wide_S : 8;
     const int ctas_per_sm[4] = {(10000 / width + kNumSMs - 1) / kNumSMs, 0, 0, 0};
@@ -484,6 +499,7 @@ int64_t csp3_lu_get_program(const csp3_lu_symbolic *sym, int which, uint8_t *buf
         case 3: P = sym->W.ok ? &sym->W.prog : nullptr; break;
         case 4: P = sym->WF.ok ? &sym->WF.prog : nullptr; break;
         case 5: P = sym->WB.ok ? &sym->WB.prog : nullptr; break;
+        case 6: P = sym->PP.ok ? &sym->PP.prog : nullptr; break;
         default: break;
     }
     if (!P) { set_error("lu_get_program: program %d not available", which); return CSP3_ERR_ARG; }
@@ -494,6 +510,10 @@ int64_t csp3_lu_get_program(const csp3_lu_symbolic *sym, int which, uint8_t *buf
             geometry[1] = sym->W.width; geometry[2] = sym->W.acc_slots; geometry[3] = sym->W.ring_entries;
             geometry[4] = sym->W.stage_entries; geometry[5] = sym->W.records; geometry[6] = (i64)sym->W.smem_bytes;
             geometry[7] = sym->W.groups;
+        }
+        if (which == 6) {
+            geometry[1] = sym->PP.width; geometry[2] = sym->PP.nslots; geometry[3] = sym->PP.npanels; geometry[4] = sym->PP.ops;
+            geometry[5] = sym->PP.steps; geometry[6] = (i64)sym->PP.smem_bytes; geometry[7] = sym->PP.groups;
         }
         if (which == 4 || which == 5) {
             const WideSweep &Wsw = which == 4 ? sym->WF : sym->WB;
@@ -556,6 +576,7 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
     const bool wsolve = sym->W.ok && sym->WF.ok && sym->WB.ok;
     const size_t i_wfs = add(sym->WF.prog.bytes.data(), wsolve ? sym->WF.prog.bytes.size() : 0);
     const size_t i_wbs = add(sym->WB.prog.bytes.data(), wsolve ? sym->WB.prog.bytes.size() : 0);
+    const size_t i_prf = add(sym->PP.prog.bytes.data(), sym->PP.ok ? sym->PP.prog.bytes.size() : 0);
     const size_t i_pinv = add(F.pinv.data(), wsolve ? F.pinv.size() * 4 : 0);
     const size_t i_qinv = add(sym->qinv.data(), wsolve ? sym->qinv.size() * 4 : 0);
     total = (total + 255) & ~(size_t)255;
@@ -587,6 +608,11 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
             D.wbs_records = sym->WB.records; D.wbs_nslots = sym->WB.nslots; D.wbs_smem = sym->WB.smem_bytes;
             D.d_pinv = (const i32 *)at(i_pinv); D.d_qinv = (const i32 *)at(i_qinv);
         }
+    }
+    if (sym->PP.ok && sym->PP.smem_bytes <= (size_t)200 * 1024) {
+        D.panel_ok = true;
+        D.prf_prog = (const uint8_t *)at(i_prf); D.prf_prog_bytes = (i32)sym->PP.prog.bytes.size();
+        D.prf_nslots = sym->PP.nslots; D.prf_steps = sym->PP.steps; D.prf_smem = sym->PP.smem_bytes;
     }
     D.ready = true;
     return 0;

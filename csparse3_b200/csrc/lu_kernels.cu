@@ -429,8 +429,15 @@ bool use_wide(const DevSchedule &D, i64 batch)
     return D.wide_ok && tuning().wide != 0 && tuning().ws_S == 0;
 }
 
+bool use_panel(const DevSchedule &D, i64 batch)
+{
+    (void)batch;
+    return D.panel_ok && tuning().panel != 0 && tuning().ws_S == 0 && (!D.wide_ok || D.wide_S == 8);
+}
+
 int workspace_bundle_width(const DevSchedule &D, i64 batch)
 {
+    if (use_panel(D, batch)) return 8;
     if (use_wide(D, batch)) return D.wide_S;
     const int S = tuning().ws_S;
     if (S == 2 || S == 4 || S == 8 || S == 16) return S;
@@ -445,6 +452,7 @@ int launch_refactor(const DevSchedule &D, i64 batch, const double *Ax, double *L
                     bool interleaved, cudaStream_t st)
 {
     if (batch <= 0) return 0;
+    if (interleaved && use_panel(D, batch)) return launch_refactor_panel(D, batch, Ax, Lx, Ux, status, nullptr, st);
     if (interleaved && use_wide(D, batch)) return launch_refactor_wide(D, batch, Ax, Lx, Ux, status, st);
     RefactorArgs a;
     a.prog = D.rf_prog; a.prog_bytes = D.rf_prog_bytes; a.prog_stage = D.rf_prog_stage;
