@@ -37,6 +37,7 @@ Tuning &tuning()
         v.wide_budget = env("CSP3_WIDE_BUDGET");
         if (getenv("CSP3_PANEL")) v.panel = env("CSP3_PANEL");
         v.panel_fma = env("CSP3_PANEL_FMA");
+        v.panel_budget = env("CSP3_PANEL_BUDGET");
         return v;
     }();
     return t;
@@ -120,12 +121,17 @@ static void compile_wide(csp3_lu_symbolic &Sy)
         Sy.qinv.assign((size_t)Sy.n, 0);
         for (i64 i = 0; i < Sy.n; ++i) Sy.qinv[(size_t)(Sy.q.empty() ? i : Sy.q[(size_t)i])] = (i32)i;
     }
-    if (t.panel != 0 && Sy.n > 0) {
+    if (Sy.n > 0) {          // compiled always (cheap), executed only with CSP3_PANEL=1: the wide kernel is faster today
         const char *why = "";
-        if (!compile_panel_refactor(Sy.n, Sy.Ap.data(), Sy.Ai.data(), Sy.q, Sy.F, 8, 4, Sy.PP, &why)) {
-            if (getenv("CSP3_DEBUG")) fprintf(stderr, "csp3: panel refactor unavailable: %s\n", why);
-            Sy.PP = PanelProgram();
+        // 9 one-warp CTAs per SM keep every bundle of a 10,000-system batch resident (1,250 bundles on 148 SMs)
+        const size_t panel_budget = t.panel_budget > 0 ? (size_t)t.panel_budget : (((size_t)227 * 1024 / 9 - 1024) & ~(size_t)63);
+        bool ok = false;
+        for (int i = 0; i < 4 && !ok; ++i) {                       // patterns with long columns: fewer resident bundles
+            ok = compile_panel_refactor(Sy.n, Sy.Ap.data(), Sy.Ai.data(), Sy.q, Sy.F, 8, std::min<size_t>(panel_budget << i, (size_t)200 * 1024), Sy.PP, &why);
+            if (!ok && getenv("CSP3_DEBUG")) fprintf(stderr, "csp3: panel refactor unavailable at budget %zu: %s\n", panel_budget << i, why);
+            if (t.panel_budget > 0) break;
         }
+        if (!ok) Sy.PP = PanelProgram();
     }
     if (t.wide == 0 || Sy.n == 0) return;
     const i32 width = (t.wide_S == 4 || t.wide_S == 16 || t.wide_S == 32) ? t.wide_S : 8;
@@ -512,7 +518,7 @@ int64_t csp3_lu_get_program(const csp3_lu_symbolic *sym, int which, uint8_t *buf
             geometry[7] = sym->W.groups;
         }
         if (which == 6) {
-            geometry[1] = sym->PP.width; geometry[2] = sym->PP.nslots; geometry[3] = sym->PP.npanels; geometry[4] = sym->PP.ops;
+            geometry[0] = sym->PP.ring; geometry[1] = sym->PP.width; geometry[2] = sym->PP.nslots; geometry[3] = sym->PP.landing; geometry[4] = sym->PP.ops;
             geometry[5] = sym->PP.steps; geometry[6] = (i64)sym->PP.smem_bytes; geometry[7] = sym->PP.groups;
         }
         if (which == 4 || which == 5) {
@@ -612,7 +618,7 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
     if (sym->PP.ok && sym->PP.smem_bytes <= (size_t)200 * 1024) {
         D.panel_ok = true;
         D.prf_prog = (const uint8_t *)at(i_prf); D.prf_prog_bytes = (i32)sym->PP.prog.bytes.size();
-        D.prf_nslots = sym->PP.nslots; D.prf_steps = sym->PP.steps; D.prf_smem = sym->PP.smem_bytes;
+        D.prf_nslots = sym->PP.nslots; D.prf_lsrc = sym->PP.ring + sym->PP.landing; D.prf_steps = sym->PP.steps; D.prf_smem = sym->PP.smem_bytes;
     }
     D.ready = true;
     return 0;

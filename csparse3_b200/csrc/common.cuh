@@ -48,7 +48,7 @@ struct DevSchedule {
     // panel refactor program (lu_panel.cu), bundles of 8 systems
     bool panel_ok = false;
     const uint8_t *prf_prog = nullptr;
-    i32 prf_prog_bytes = 0, prf_nslots = 0, prf_steps = 0;
+    i32 prf_prog_bytes = 0, prf_nslots = 0, prf_steps = 0, prf_lsrc = 0;
     size_t prf_smem = 0;
     void *arena = nullptr;             // single allocation backing all of the above
     size_t arena_bytes = 0;
@@ -76,7 +76,7 @@ int launch_solve_wide(const DevSchedule &D, i64 batch, const double *Lw, const d
 // 0 = automatic)
 struct Tuning {
     int rf_S = 0, sv_S = 0, ws_S = 0, rf_win = 0, sv_stage = 0;
-    int panel = 1, panel_fma = 0;          // CSP3_PANEL (0 disables the panel refactor kernel), CSP3_PANEL_FMA (fused multiply-add, not bit-exact)
+    int panel = 0, panel_fma = 0, panel_budget = 0;          // CSP3_PANEL=1 selects the experimental panel refactor kernel (lu_panel.cu), CSP3_PANEL_FMA (fused multiply-add, not bit-exact)
     int wide = 1, wide_solve = 1, wide_S = 0, wide_R = 0, wide_ring = 0, wide_stage = 0, wide_budget = 0;   // CSP3_WIDE (0 disables), CSP3_WIDE_S/_R/_F/_BUDGET
 };
 Tuning &tuning();

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--batch", type=int, default=10000)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--distinct", type=int, default=64)
+    ap.add_argument("--check", type=int, default=4, help="systems compared with the oracle (0: none)")
     args = ap.parse_args()
     import torch
     import bench
@@ -41,6 +42,17 @@ def main():
         torch.cuda.synchronize()
         print("iter %d: refactor %.3f ms, solve %.3f ms" % (it, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])), flush=True)
     assert int(st.abs().max().item()) == 0
+    if args.check:
+        from oracle import oracle as orc
+        xs = x[:args.check].cpu().numpy()
+        worst = 0.0
+        exact = True
+        for k in range(args.check):
+            Lx, Ux = orc.csc_lu_refactor(n, Ap, Ai, Ax[k], sym.q, sym.pinv, sym.Lp, sym.Li, sym.Up, sym.Ui)
+            xo = orc.csc_lu_solve(n, sym.Lp, sym.Li, Lx, sym.Up, sym.Ui, Ux, sym.pinv, sym.q, b[k])
+            exact = exact and np.array_equal(xs[k], xo)
+            worst = max(worst, float(np.linalg.norm(xs[k] - xo) / np.linalg.norm(xo)))
+        print("check vs oracle: bit-exact %s, worst relative difference %.3e" % (exact, worst), flush=True)
 
 
 if __name__ == "__main__":
