@@ -67,8 +67,15 @@ SIGNATURES = {
     "csp3_lu_refactor_host": [vp, i64, vp, vp, vp, vp],
     "csp3_lu_solve_host": [vp, i64, vp, vp, vp, vp],
     "csp3_csc_lusol_host": [i64, i64, vp, vp, vp, vp, f64],
+    "csp3_nr_create": [i64, i64, vp, vp, vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, vp, vp, C.POINTER(vp)],
+    "csp3_nr_destroy": [vp],
+    "csp3_nr_workspace_bytes": [vp, i64],
+    "csp3_nr_jacobian": [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "csp3_nr_solve": [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp],
+    "csp3_nr_solve_host": [vp, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp],
 }
-_RESTYPE = {"csp3_last_error_string": C.c_char_p, "csp3_lu_workspace_bytes": i64, "csp3_lu_get_program": i64}
+_RESTYPE = {"csp3_last_error_string": C.c_char_p, "csp3_lu_workspace_bytes": i64, "csp3_lu_get_program": i64,
+             "csp3_nr_workspace_bytes": i64}
 
 _lib = None
 

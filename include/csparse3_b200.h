@@ -221,6 +221,46 @@ int csp3_lu_solve_host(csp3_lu_symbolic *sym, int64_t batch, const double *Lx, c
 int csp3_csc_lusol_host(int64_t order, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
                         double *b, double tol);
 
+/* ---- Newton-Raphson power-flow iteration on the device -------------------- */
+/* The consumer loop the reference's pieces exist for: J = pack_4_by_4(H, N, M, L)
+ * (src/CSparse3/csc.py:588-606 -> csc_stack_4_by_4_ff csc_numba.py:640-720), mismatch from Ybus * V
+ * (CscMat.__mul__ on a vector, csc.py:374-379 -> csc_matvec), then factor, solve, update.  The reference runs each
+ * piece on the host for one case; this plan keeps a batch of same-topology cases on the GPU for whole iterations:
+ * evaluate I = Ybus V and the mismatch, write the four polar Jacobian blocks straight into the refactorisation's
+ * value array (the block stacking is a precomputed entry map), refactor, solve, update (vm, va).
+ *
+ *   Ybus        CSR pattern y_rowptr[n_bus+1], y_col[nnz_y], complex values y_val[nnz_y] (re, im interleaved)
+ *   pvpq, pq    bus indices of the angle unknowns / magnitude unknowns; n = npvpq + npq equations:
+ *               P mismatch of pvpq buses, then Q mismatch of pq buses (the order of the Jacobian's rows and columns)
+ *   Jacobian    entry p of the CSC value array (the pattern `sym` was analysed with) is block j_block[p]
+ *               (0 dP/dVa, 1 dP/dVm, 2 dQ/dVa, 3 dQ/dVm) evaluated at Ybus entry j_ent[p]
+ *   branches    optional N-1 support: case c with out_branch[c] = k >= 0 subtracts br_val[q][k] from Ybus entry
+ *               br_slot[q][k], q = 0..3 (ff, ft, tf, tt contributions of branch k); arrays are [4][n_branch]
+ * All pointers of csp3_nr_create are HOST pointers; the plan keeps device copies on the current device and uses `sym`
+ * (which must outlive it). */
+typedef struct csp3_nr_plan csp3_nr_plan;
+int csp3_nr_create(int64_t n_bus, int64_t nnz_y, const int32_t *y_rowptr, const int32_t *y_col, const double *y_val,
+                   int64_t npvpq, const int32_t *pvpq, int64_t npq, const int32_t *pq, int64_t jnnz, const int32_t *j_ent,
+                   const int32_t *j_block, int64_t n_branch, const int32_t *br_slot, const double *br_val,
+                   csp3_lu_symbolic *sym, csp3_nr_plan **plan);
+int csp3_nr_destroy(csp3_nr_plan *plan);
+int64_t csp3_nr_workspace_bytes(const csp3_nr_plan *plan, int64_t batch);
+/* Jacobian values Ax[batch, jnnz] and right-hand side b[batch, n] = -(S_calc - S_spec) at the state (vm, va)
+ * [batch, n_bus]; fnorm[batch] = max |mismatch|.  sspec[batch, n]: specified P of the pvpq buses, then Q of the pq
+ * buses.  out_branch[batch] may be NULL.  DEVICE pointers, stream-ordered. */
+int csp3_nr_jacobian(const csp3_nr_plan *plan, int64_t batch, const double *vm, const double *va, const int32_t *out_branch,
+                     const double *sspec, double *Ax, double *b, double *fnorm, void *work, void *stream);
+/* `iters` Newton iterations (each: evaluate, refactor, solve, update) on (vm, va) in place; fnorm = max |mismatch|
+ * at the returned state; status = the last refactorisation's (0 ok, k+1 = bad pivot in column k).  DEVICE pointers. */
+int csp3_nr_solve(const csp3_nr_plan *plan, int64_t batch, int64_t iters, const double *sspec, const int32_t *out_branch,
+                  double *vm, double *va, double *fnorm, int32_t *status, void *work, void *stream);
+/* Host-buffer form (chunked H2D -> iterations -> D2H pipeline on internal streams).  The start state is vm0 / va0:
+ * one vector shared by all cases (start_stride = 0, e.g. a flat start) or one per case (start_stride = n_bus).
+ * Per case only sspec travels to the device and (vm, va, fnorm, status) come back. */
+int csp3_nr_solve_host(csp3_nr_plan *plan, int64_t batch, int64_t iters, const double *sspec, const int32_t *out_branch,
+                       const double *vm0, const double *va0, int64_t start_stride, double *vm, double *va, double *fnorm,
+                       int32_t *status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from csparse3_b200.dist import gather_solutions, shard_range
+from csparse3_b200.dist import gather_solutions, gather_to_root, shard_range
 
 
 def _free_port():
@@ -24,6 +24,8 @@ def _worker(rank, world, port, batch, n, out_dir):
     full = torch.arange(batch * n, dtype=torch.float64).reshape(batch, n)
     x = gather_solutions(full[start:stop].clone(), batch)
     ok = bool(torch.equal(x, full))
+    xr = gather_to_root(full[start:stop].clone(), batch)
+    ok = ok and ((xr is None) if rank != 0 else bool(torch.equal(xr, full)))
     np.save(os.path.join(out_dir, "ok%d.npy" % rank), np.array([ok, start, stop]))
     dist.destroy_process_group()
 
