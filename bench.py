@@ -129,10 +129,20 @@ def make_inputs(case, wl, start, count, pinned):
     return Ax, b
 
 
+def nr_base_state(case):
+    """Operating point the time series / the outage sweep moves around: the shared start vector of every case."""
+    Vb = case.voltages([case.seed + 7])[0]
+    return np.abs(Vb), np.angle(Vb)
+
+
 def nr_targets(case, wl, start, count):
-    """Specified injections of the global cases [start, start+count): S_calc at seeded 'true' voltages, so every case
-    has a solution near the flat start.  -> (sspec[count, n], out_branch[count] or None)   (numpy only)"""
+    """Specified injections of the global cases [start, start+count): S_calc at a seeded perturbation of the base state
+    (angles +- N(0, 0.01) rad, PQ magnitudes x (1 + N(0, 0.005)); PV / slack magnitudes and the slack angle are the
+    specified ones), so every case has a solution a few Newton steps away from the shared start.
+    -> (sspec[count, n], out_branch[count] or None)   (numpy only)"""
     ids = start + np.arange(count)
+    N = case.n_bus
+    vmb, vab = nr_base_state(case)
     ob = None
     Y = case.ybus_values()
     if wl["kind"] == "outage":
@@ -141,8 +151,15 @@ def nr_targets(case, wl, start, count):
     sspec = np.empty((count, case.n))
     for s in range(0, count, 512):
         sl = slice(s, min(s + 512, count))
-        Vt = case.voltages(5000 + ids[sl])
-        Yb = case.ybus_values(ob[sl]) if ob is not None else np.broadcast_to(Y, (Vt.shape[0], case.nnz_y))
+        c = sl.stop - sl.start
+        vm = np.empty((c, N)); va = np.empty((c, N))
+        for r, k in enumerate(ids[sl]):
+            rng = np.random.default_rng(int(5000 + k))
+            va[r] = vab + rng.normal(0.0, 0.01, N)
+            vm[r] = vmb * (1.0 + rng.normal(0.0, 0.005, N))
+        vm[:, case.pv] = vmb[case.pv]; vm[:, 0] = vmb[0]; va[:, 0] = vab[0]
+        Vt = vm * np.exp(1j * va)
+        Yb = case.ybus_values(ob[sl]) if ob is not None else np.broadcast_to(Y, (c, case.nnz_y))
         I = np.add.reduceat(Yb * Vt[:, case.yk], case.y_rowstart, axis=1)
         S = Vt * np.conj(I)
         sspec[sl] = np.concatenate([S[:, case.pvpq].real, S[:, case.pq].imag], axis=1)
@@ -423,9 +440,10 @@ def main():
     va_h = torch.empty((B, case.n_bus), dtype=torch.float64, pin_memory=True)
     fn_h = torch.empty(B, dtype=torch.float64, pin_memory=True)
     nst_h = torch.empty(B, dtype=torch.int32, pin_memory=True)
-    nr_args = dict(iters=args.nr_iters, out_branch=ob_np, vm=vm_h.numpy(), va=va_h.numpy(), fnorm=fn_h.numpy(), status=nst_h.numpy())
+    vm0, va0 = nr_base_state(case)
+    nr_args = dict(iters=args.nr_iters, out_branch=ob_np, vm0=vm0, va0=va0, vm=vm_h.numpy(), va=va_h.numpy(), fnorm=fn_h.numpy(), status=nst_h.numpy())
     warm = min(B, 512)
-    plan.solve_host(sspec_h.numpy()[:warm], iters=1, out_branch=None if ob_np is None else ob_np[:warm])       # staging set-up
+    plan.solve_host(sspec_h.numpy()[:warm], iters=1, out_branch=None if ob_np is None else ob_np[:warm], vm0=vm0, va0=va0)       # staging set-up
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
@@ -434,6 +452,7 @@ def main():
     nr_s = (time.perf_counter() - t0) / args.e2e_steps
     assert (nst_h.numpy() == 0).all(), "Newton-Raphson: a case reported a bad pivot"
     nr_fnorm = float(fn_h.numpy().max())
+    assert nr_fnorm < 1e-3, "Newton-Raphson did not converge (max mismatch %g)" % nr_fnorm
     # (2) the plain LU host call (values of every Jacobian over PCIe), for comparison
     Ax_np, b_np, x_np, st_np = Ax_h.numpy(), b_h.numpy(), x_h.numpy(), st_h.numpy()
     sym.refactor_solve_host(Ax_np[:warm], b_np[:warm], x_np[:warm], st_np[:warm])

@@ -18,6 +18,7 @@ def _case(nb):
 def _targets(case, B, Y=None):
     """Specified injections = S_calc at seeded 'true' voltages (so every case has a solution near the flat start)."""
     Vt = case.voltages(5000 + np.arange(B))
+    Vt[:, case.pv] /= np.abs(Vt[:, case.pv]); Vt[:, 0] = 1.0          # consistent with a flat start: |V| = 1 at PV buses and the slack
     Yb = np.broadcast_to(case.ybus_values() if Y is None else Y, (B, case.nnz_y))
     S, _ = nro.s_calc(case, Vt, Yb)
     return np.ascontiguousarray(np.concatenate([S[:, case.pvpq].real, S[:, case.pq].imag], axis=1)), Vt
@@ -82,6 +83,7 @@ def test_nr_solve_time_series_vs_oracle():
     assert (fnorm < 1e-9).all() and (fnorm_o < 1e-9).all()
     # converged to the voltages the injections were computed from
     assert np.abs(vm * np.exp(1j * va) - Vt).max() < 1e-8
+    assert np.array_equal(vm[:, case.pv], np.ones((B, len(case.pv)))) and (va[:, 0] == 0).all()
 
 
 @pytest.mark.gpu
