@@ -40,6 +40,7 @@ SIGNATURES = {
     "csp3_spgemm_symbolic": [i64, i64, vp, vp, i64, i64, vp, vp, vp, C.POINTER(i64), vp],
     "csp3_spgemm_numeric": [i64, i64, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp],
     "csp3_csc_plusminus_host": [i64, i64, vp, vp, vp, vp, vp, vp, f64, vp, vp, vp],
+    "csp3_csc_add_ff_host": [i64, i64, vp, vp, vp, vp, vp, vp, f64, f64, vp, vp, vp],
     "csp3_stack4_create": [i64, i64, vp, vp, i64, i64, vp, vp, i64, i64, vp, vp, i64, i64, vp, vp, C.POINTER(vp)],
     "csp3_stack4_destroy": [vp],
     "csp3_stack4_sizes": [vp, vp],
@@ -63,6 +64,7 @@ SIGNATURES = {
     "csp3_lu_refactor_solve_batched": [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp],
     "csp3_lu_refactor_ws": [vp, i64, vp, vp, vp, vp],
     "csp3_lu_solve_ws": [vp, i64, vp, vp, vp, vp],
+    "csp3_lu_growth_ws": [vp, i64, vp, vp, vp],
     "csp3_lu_refactor_solve_host": [vp, i64, vp, vp, vp, vp],
     "csp3_lu_refactor_host": [vp, i64, vp, vp, vp, vp],
     "csp3_lu_solve_host": [vp, i64, vp, vp, vp, vp],

@@ -23,6 +23,7 @@ from ._lib import as_f64, as_i32, check, ptr
 
 __all__ = [
     "csc_mat_vec_ff", "csc_multiply_ff", "csc_transpose", "csc_to_csr", "csc_cumsum_i", "sptools",
+    "csc_add_ff", "csc_scatter_f", "csc_scatter_ff", "csc_spalloc_f", "csc_sprealloc_f", "ialloc", "xalloc",
     "csc_amd", "csc_etree", "csc_post", "csc_lu", "csc_lu_refactor", "csc_lu_solve", "csc_lusol",
     "csc_to_dense", "csc_diagonal", "csc_diagonal_from_array", "csc_stack_4_by_4_ff", "csc_sub_matrix",
     "csc_sub_matrix_cols", "csc_sub_matrix_rows", "csc_norm", "find_islands", "coo_to_csc",
@@ -86,6 +87,71 @@ def csc_cumsum_i(p, c, n):
     p[0] = 0
     c[:n] = p[:n]
     return int(p[n])
+
+
+def ialloc(n):
+    """csc_numba.py:36-38"""
+    return np.zeros(n, dtype=np.int32)
+
+
+def xalloc(n):
+    """csc_numba.py:41-43"""
+    return np.zeros(n, dtype=np.float64)
+
+
+def csc_spalloc_f(m, n, nzmax):
+    """Allocate an empty CSC matrix -> (m, n, indptr, indices, data, nzmax).  csc_numba.py:46-60 (cs_spalloc);
+    allocation bookkeeping on the host, there is nothing to run on the device."""
+    nzmax = max(int(nzmax), 1)
+    return m, n, ialloc(n + 1), ialloc(nzmax), xalloc(nzmax), nzmax
+
+
+def csc_sprealloc_f(An, Aindptr, Aindices, Adata, nzmax):
+    """Change the capacity of a CSC matrix -> (indices, data, nzmax).  csc_numba.py:97-122 (cs_sprealloc); the entries
+    beyond the old length are uninitialised in the reference (np.empty), zero here."""
+    if nzmax <= 0:
+        nzmax = int(Aindptr[An])
+    Ai = np.zeros(nzmax, dtype=np.int32)
+    Ax = np.zeros(nzmax, dtype=np.float64)
+    k = min(nzmax, len(Aindices)); Ai[:k] = Aindices[:k]
+    k = min(nzmax, len(Adata)); Ax[:k] = Adata[:k]
+    return Ai, Ax, nzmax
+
+
+def csc_scatter_f(Ap, Ai, Ax, j, beta, w, x, mark, Ci, nz):
+    """x += beta * A(:,j) with pattern tracking (cs_scatter).  csc_numba.py:125-151: a one-column host helper of the
+    reference's own add / multiply loops (w, x, Ci are updated in place; returns the new nz).  The batched work those
+    loops do runs on the device in csc_add_ff / csc_multiply_ff; this helper is kept for callers that drive it by hand."""
+    Ap, Ai, Ax = as_i32(Ap, "Ap"), as_i32(Ai, "Ai"), as_f64(Ax, "Ax")
+    for p in range(int(Ap[j]), int(Ap[j + 1])):
+        i = int(Ai[p])
+        if w[i] < mark:
+            w[i] = mark
+            Ci[nz] = i
+            nz += 1
+            x[i] = beta * Ax[p]
+        else:
+            x[i] += beta * Ax[p]
+    return nz
+
+
+csc_scatter_ff = csc_scatter_f          # csc_numba.py:154-180: the same kernel under its second name
+
+
+def csc_add_ff(Am, An, Aindptr, Aindices, Adata, Bm, Bn, Bindptr, Bindices, Bdata, alpha, beta):
+    """C = alpha*A + beta*B -> (Cm, Cn, Cp, Ci, Cx).  Reference: csc_numba.py:183-219 -- first-touch row order inside a
+    column, explicit zeros kept, Ci / Cx returned at their allocated length nnz(A) + nnz(B) (>= 1) with a zero tail,
+    exactly as the reference hands them back."""
+    Ap, Ai, Ax = as_i32(Aindptr, "Aindptr"), as_i32(Aindices, "Aindices"), as_f64(Adata, "Adata")
+    Bp, Bi, Bx = as_i32(Bindptr, "Bindptr"), as_i32(Bindices, "Bindices"), as_f64(Bdata, "Bdata")
+    m, n = int(Am), int(Bn)
+    cap = max(int(Ap[An]) + int(Bp[n]), 1)
+    Cp = np.zeros(n + 1, dtype=np.int32)
+    Ci = np.zeros(cap, dtype=np.int32)
+    Cx = np.zeros(cap, dtype=np.float64)
+    check(_lib.lib().csp3_csc_add_ff_host(m, n, ptr(Ap), ptr(Ai), ptr(Ax), ptr(Bp), ptr(Bi), ptr(Bx), float(alpha), float(beta),
+                                          ptr(Cp), ptr(Ci), ptr(Cx)), "csc_add_ff")
+    return m, n, Cp, Ci, Cx
 
 
 class _SpTools:

@@ -383,6 +383,28 @@ int csp3_csc_plusminus_host(int64_t m, int64_t n, const int32_t *Ap, const int32
     return 0;
 }
 
+int csp3_csc_add_ff_host(int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                         const int32_t *Bp, const int32_t *Bi, const double *Bx, double alpha, double beta, int32_t *Cp,
+                         int32_t *Ci, double *Cx)
+{
+    if (m < 0 || n < 0 || !Ap || !Bp || !Cp) { set_error("csc_add_ff: bad arguments"); return CSP3_ERR_ARG; }
+    if (int rc = require_device()) return rc;
+    const i64 na = Ap[n], nb = Bp[n];
+    Dev dAp, dAi, dAx, dBp, dBi, dBx, dCp, dCi, dCx;
+    CSP3_TRY(dAp.put(Ap, (size_t)(n + 1) * 4)); CSP3_TRY(dAi.put(Ai, (size_t)na * 4)); CSP3_TRY(dAx.put(Ax, (size_t)na * 8));
+    CSP3_TRY(dBp.put(Bp, (size_t)(n + 1) * 4)); CSP3_TRY(dBi.put(Bi, (size_t)nb * 4)); CSP3_TRY(dBx.put(Bx, (size_t)nb * 8));
+    CSP3_TRY(dCp.alloc((size_t)(n + 1) * 4)); CSP3_TRY(dCi.alloc((size_t)(na + nb) * 4)); CSP3_TRY(dCx.alloc((size_t)(na + nb) * 8));
+    int rc = csc_add_ff_device(m, n, dAp.as<i32>(), dAi.as<i32>(), dAx.as<double>(), dBp.as<i32>(), dBi.as<i32>(),
+                               dBx.as<double>(), alpha, beta, dCp.as<i32>(), dCi.as<i32>(), dCx.as<double>(), nullptr);
+    if (rc) return rc;
+    CSP3_CUDA(cudaDeviceSynchronize());
+    CSP3_TRY(dCp.get(Cp, (size_t)(n + 1) * 4));
+    const i64 nc = Cp[n];
+    CSP3_TRY(dCi.get(Ci, (size_t)nc * 4));
+    CSP3_TRY(dCx.get(Cx, (size_t)nc * 8));
+    return 0;
+}
+
 // ---- host symbolic ----------------------------------------------------------------------------------------
 int csp3_csc_amd(int64_t order, int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, int32_t *q)
 {
@@ -583,6 +605,9 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
     const size_t i_wfs = add(sym->WF.prog.bytes.data(), wsolve ? sym->WF.prog.bytes.size() : 0);
     const size_t i_wbs = add(sym->WB.prog.bytes.data(), wsolve ? sym->WB.prog.bytes.size() : 0);
     const size_t i_prf = add(sym->PP.prog.bytes.data(), sym->PP.ok ? sym->PP.prog.bytes.size() : 0);
+    std::vector<uint8_t> ldiag(F.Li.size(), 0);
+    for (i64 k = 0; k < sym->n; ++k) ldiag[(size_t)F.Lp[(size_t)k]] = 1;
+    const size_t i_ldiag = add(ldiag.data(), ldiag.size());
     const size_t i_pinv = add(F.pinv.data(), wsolve ? F.pinv.size() * 4 : 0);
     const size_t i_qinv = add(sym->qinv.data(), wsolve ? sym->qinv.size() * 4 : 0);
     total = (total + 255) & ~(size_t)255;
@@ -620,6 +645,7 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
         D.prf_prog = (const uint8_t *)at(i_prf); D.prf_prog_bytes = (i32)sym->PP.prog.bytes.size();
         D.prf_nslots = sym->PP.nslots; D.prf_lsrc = sym->PP.ring + sym->PP.landing; D.prf_steps = sym->PP.steps; D.prf_smem = sym->PP.smem_bytes;
     }
+    D.d_ldiag = (const uint8_t *)at(i_ldiag);
     D.ready = true;
     return 0;
 }
@@ -691,6 +717,16 @@ int csp3_lu_solve_ws(const csp3_lu_symbolic *sym, int64_t batch, void *work, con
     double *Lw, *Uw, *z;
     carve_workspace(*D, batch, work, &Lw, &Uw, &z);
     return launch_solve(*D, batch, Lw, Uw, b, x, z, true, (cudaStream_t)stream);
+}
+
+int csp3_lu_growth_ws(const csp3_lu_symbolic *sym, int64_t batch, const void *work, double *growth, void *stream)
+{
+    const DevSchedule *D = current_schedule(sym);
+    if (!D) return CSP3_ERR_ARG;
+    if (batch < 0 || !work || !growth) { set_error("lu_growth_ws: bad arguments"); return CSP3_ERR_ARG; }
+    double *Lw, *Uw, *z;
+    carve_workspace(*D, batch, const_cast<void *>(work), &Lw, &Uw, &z);
+    return launch_growth(*D, batch, Lw, growth, (cudaStream_t)stream);
 }
 
 int csp3_lu_refactor_solve_batched(const csp3_lu_symbolic *sym, int64_t batch, const double *Ax,

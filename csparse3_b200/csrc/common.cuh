@@ -45,6 +45,7 @@ struct DevSchedule {
     i32 wbs_prog_bytes = 0, wbs_prog_stage = 0, wbs_records = 0, wbs_nslots = 0;
     size_t wfs_smem = 0, wbs_smem = 0;
     const i32 *d_pinv = nullptr, *d_qinv = nullptr;
+    const uint8_t *d_ldiag = nullptr;     // 1 at the unit-diagonal positions of L (never written in the workspace layout)
     // panel refactor program (lu_panel.cu), bundles of 8 systems
     bool panel_ok = false;
     const uint8_t *prf_prog = nullptr;
@@ -66,6 +67,7 @@ bool use_wide(const DevSchedule &D, i64 batch);
 int launch_refactor_wide(const DevSchedule &D, i64 batch, const double *Ax, double *Lw, double *Uw, i32 *status,
                          cudaStream_t st);
 bool use_panel(const DevSchedule &D, i64 batch);
+int launch_growth(const DevSchedule &D, i64 batch, const double *Lw, double *growth, cudaStream_t st);
 int launch_refactor_panel(const DevSchedule &D, i64 batch, const double *Ax, double *Lw, double *Uw, i32 *status,
                           double *growth, cudaStream_t st);
 int launch_solve_wide(const DevSchedule &D, i64 batch, const double *Lw, const double *Uw, const double *b, double *x,

@@ -527,6 +527,43 @@ __global__ void k_csc_add(int n, const i32 *__restrict__ Ap, const i32 *__restri
     }
 }
 
+// ---- C = alpha*A + beta*B in the reference's own kernel's form (csc_add_ff, src/CSparse3/csc_numba.py:183-219) ----
+// Column j scatters alpha*A(:,j), then beta*B(:,j) into a dense accumulator: x[i] = coef*v at the first touch of row
+// i, x[i] += coef*v afterwards; the pattern is emitted in FIRST-TOUCH order, explicit zeros are kept, duplicates are
+// summed.  One thread per column; a row's value is accumulated in exactly that order with unfused multiply / add,
+// so the result is bit-identical to the reference's (numba compiles it without fast-math).
+template <bool FILL>
+__global__ void k_csc_add_ff(int n, const i32 *__restrict__ Ap, const i32 *__restrict__ Ai, const double *__restrict__ Ax,
+                             const i32 *__restrict__ Bp, const i32 *__restrict__ Bi, const double *__restrict__ Bx,
+                             double alpha, double beta, i32 *cnt, const i32 *__restrict__ Cp, i32 *Ci, double *Cx)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int a0 = __ldg(Ap + j), a1 = __ldg(Ap + j + 1), b0 = __ldg(Bp + j), b1 = __ldg(Bp + j + 1);
+        const int la = a1 - a0, total = la + (b1 - b0);
+        int out = FILL ? __ldg(Cp + j) : 0;
+        for (int t = 0; t < total; ++t) {
+            const int r = (t < la) ? __ldg(Ai + a0 + t) : __ldg(Bi + b0 + t - la);
+            bool seen = false;
+            for (int u = 0; u < t && !seen; ++u) seen = ((u < la) ? __ldg(Ai + a0 + u) : __ldg(Bi + b0 + u - la)) == r;
+            if (seen) continue;
+            if (FILL) {
+                double x = 0.0;
+                bool first = true;
+                for (int u = t; u < total; ++u) {
+                    const int ru = (u < la) ? __ldg(Ai + a0 + u) : __ldg(Bi + b0 + u - la);
+                    if (ru != r) continue;
+                    const double term = (u < la) ? __dmul_rn(alpha, __ldg(Ax + a0 + u)) : __dmul_rn(beta, __ldg(Bx + b0 + u - la));
+                    x = first ? term : __dadd_rn(x, term);
+                    first = false;
+                }
+                Ci[out] = r; Cx[out] = x;
+            }
+            ++out;
+        }
+        if (!FILL) cnt[j] = out;
+    }
+}
+
 inline int grid_for(i64 work, int per_block, int cap = kNumSMs * 16)
 {
     const i64 g = (work + per_block - 1) / per_block;
@@ -733,6 +770,22 @@ int csc_add_device(i64 m, i64 n, const i32 *Ap, const i32 *Ai, const double *Ax,
     k_csc_add<false><<<grid_for(n, kThreads), kThreads, 0, st>>>((int)n, Ap, Ai, Ax, Bp, Bi, Bx, sign, cnt.as<i32>(), nullptr, nullptr, nullptr);
     if (scan_i32((int)n, cnt.as<i32>(), Cp, st)) { set_error("device alloc failed"); return -3; }
     k_csc_add<true><<<grid_for(n, kThreads), kThreads, 0, st>>>((int)n, Ap, Ai, Ax, Bp, Bi, Bx, sign, nullptr, Cp, Ci, Cx);
+    CSP3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// C = alpha*A + beta*B, reference csc_add_ff semantics (first-touch order, zeros kept).  Cp[n+1] is filled; Ci/Cx
+// receive Cp[n] entries (caller capacity >= nnzA + nnzB).
+int csc_add_ff_device(i64 m, i64 n, const i32 *Ap, const i32 *Ai, const double *Ax, const i32 *Bp, const i32 *Bi,
+                      const double *Bx, double alpha, double beta, i32 *Cp, i32 *Ci, double *Cx, cudaStream_t st)
+{
+    (void)m;
+    if (n == 0) { CSP3_CUDA(cudaMemsetAsync(Cp, 0, 4, st)); return 0; }
+    DevBuf cnt(st);
+    if (cnt.alloc((size_t)(n + 1) * 4)) { set_error("device alloc failed"); return -3; }
+    k_csc_add_ff<false><<<grid_for(n, kThreads), kThreads, 0, st>>>((int)n, Ap, Ai, Ax, Bp, Bi, Bx, alpha, beta, cnt.as<i32>(), nullptr, nullptr, nullptr);
+    if (scan_i32((int)n, cnt.as<i32>(), Cp, st)) { set_error("device alloc failed"); return -3; }
+    k_csc_add_ff<true><<<grid_for(n, kThreads), kThreads, 0, st>>>((int)n, Ap, Ai, Ax, Bp, Bi, Bx, alpha, beta, nullptr, Cp, Ci, Cx);
     CSP3_CUDA(cudaGetLastError());
     return 0;
 }

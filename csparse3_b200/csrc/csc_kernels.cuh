@@ -27,4 +27,7 @@ int spgemm_device(bool numeric, i64 Am, i64 An, const i32 *Ap, const i32 *Ai, co
 int csc_add_device(i64 m, i64 n, const i32 *Ap, const i32 *Ai, const double *Ax, const i32 *Bp, const i32 *Bi,
                    const double *Bx, double sign, i32 *Cp, i32 *Ci, double *Cx, cudaStream_t st);
 
+int csc_add_ff_device(i64 m, i64 n, const i32 *Ap, const i32 *Ai, const double *Ax, const i32 *Bp, const i32 *Bi,
+                      const double *Bx, double alpha, double beta, i32 *Cp, i32 *Ci, double *Cx, cudaStream_t st);
+
 }  // namespace csp3

@@ -448,6 +448,36 @@ int workspace_bundle_width(const DevSchedule &D, i64 batch)
     return 16;
 }
 
+// growth[s] = max |L(i,j)|, i > j, of system s from the bundle-interleaved factor workspace: the element growth a frozen
+// pivot sequence must be watched for.  One CTA per bundle; every step reads 2 KB contiguous.
+__global__ void lu_growth_kernel(i64 batch, int lnz, int S, const uint8_t *__restrict__ ldiag, const double *__restrict__ Lw,
+                                 double *__restrict__ growth)
+{
+    __shared__ double part[256];
+    const i64 b = blockIdx.x;
+    const int s = threadIdx.x % S, q = threadIdx.x / S, nq = blockDim.x / S;
+    const double *base = Lw + (size_t)b * lnz * S + s;
+    double m = 0.0;
+    for (int e = q; e < lnz; e += nq)
+        if (!ldiag[e]) m = fmax(m, fabs(base[(size_t)e * S]));
+    part[threadIdx.x] = m;
+    __syncthreads();
+    if (q == 0) {
+        for (int t = 1; t < nq; ++t) m = fmax(m, part[t * S + s]);          // NaN-free max: a NaN factor shows up in `status`
+        const i64 g = b * S + s;
+        if (g < batch) growth[g] = m;
+    }
+}
+
+int launch_growth(const DevSchedule &D, i64 batch, const double *Lw, double *growth, cudaStream_t st)
+{
+    if (batch <= 0) return 0;
+    const int S = workspace_bundle_width(D, batch);
+    lu_growth_kernel<<<(unsigned)((batch + S - 1) / S), 256, 0, st>>>(batch, D.lnz, S, D.d_ldiag, Lw, growth);
+    CSP3_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_refactor(const DevSchedule &D, i64 batch, const double *Ax, double *Lx, double *Ux, i32 *status,
                     bool interleaved, cudaStream_t st)
 {

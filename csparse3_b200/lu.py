@@ -205,6 +205,53 @@ class LuSymbolic:
                   "csp3_lu_solve_ws")
         return x
 
+    def growth_ws(self, work, batch, growth=None):
+        """max |L(i,j)|, i > j, per system of the factors refactor_ws left in `work` (pivot-growth indicator)."""
+        import torch
+        with torch.cuda.device(work.device):
+            st = torch.cuda.current_stream().cuda_stream
+            growth = torch.empty(batch, dtype=torch.float64, device=work.device) if growth is None else growth
+            check(_lib.lib().csp3_lu_growth_ws(self._h, batch, work.data_ptr(), growth.data_ptr(), st), "csp3_lu_growth_ws")
+        return growth
+
+    def refactor_solve_checked(self, Ap, Ai, Ax, b, growth_limit=1e6, resid_tol=1e-10, work=None):
+        """Refactor + solve with the frozen pivot sequence, then VERIFY every system and re-pivot the ones that fail.
+
+        A frozen pivot sequence is only as good as the values it was chosen on: N-1 outages
+        zero entries and can make a pivot tiny.  Every system is checked on the device -- bad-pivot status, element
+        growth max |L| > growth_limit, relative residual ||A x - b|| / ||b|| > resid_tol -- and the flagged ones are
+        analysed again ON THEIR OWN VALUES (host symbolic phase: new pivot sequence and pattern) and solved through the
+        same device kernels.  Nothing is silent: the flagged system ids and what became of them are returned.
+
+        Ax [B, nnz], b [B, n]: CUDA tensors; Ap, Ai: the pattern (numpy int32).
+        -> (x [B, n], report) with report = dict(status, growth, resid, flagged=ids, resid_after=[...])"""
+        import torch
+        from .spmv import SpmvPlan
+        B = b.shape[0]
+        work = self.workspace(B, b.device) if work is None else work
+        status = self.refactor_ws(Ax, work)
+        growth = self.growth_ws(work, B)
+        x = self.solve_ws(work, b)
+        if not hasattr(self, "_spmv") or self._spmv.device != b.device:
+            self._spmv = SpmvPlan(self.n, self.n, Ap, Ai, device=b.device)
+        r = self._spmv.matvec(Ax, x)
+        resid = torch.linalg.vector_norm(r - b, dim=1) / torch.linalg.vector_norm(b, dim=1)
+        bad = (status != 0) | ~(growth <= growth_limit) | ~(resid <= resid_tol)
+        flagged = torch.nonzero(bad).flatten().cpu().numpy()
+        after = []
+        for k in flagged:
+            Axk = Ax[int(k)].cpu().numpy()
+            try:
+                symk = LuSymbolic(self.n, Ap, Ai, Axk)                   # new pivot search on this system's own values
+            except ArithmeticError:
+                after.append(float("inf"))                               # structurally / numerically singular: reported, x left as is
+                continue
+            xk, stk = symk.refactor_solve(Ax[int(k):int(k) + 1].contiguous(), b[int(k):int(k) + 1].contiguous())
+            x[int(k)] = xk[0]
+            rk = self._spmv.matvec(Ax[int(k):int(k) + 1].contiguous(), xk)
+            after.append(float(torch.linalg.vector_norm(rk[0] - b[int(k)]) / torch.linalg.vector_norm(b[int(k)])))
+        return x, dict(status=status, growth=growth, resid=resid, flagged=flagged, resid_after=after)
+
     def workspace(self, batch, device):
         import torch
         return torch.empty(_lib.lib().csp3_lu_workspace_bytes(self._h, batch), dtype=torch.uint8, device=device)

@@ -102,6 +102,14 @@ int csp3_csc_plusminus_host(int64_t m, int64_t n, const int32_t *Ap, const int32
                             const int32_t *Bp, const int32_t *Bi, const double *Bx, double sign, int32_t *Cp,
                             int32_t *Ci, double *Cx);
 
+/* C = alpha*A + beta*B in the form of the reference's own kernel csc_add_ff, src/CSparse3/csc_numba.py:183-219
+ * (csc_scatter_f :125-151): per column alpha*A(:,j) then beta*B(:,j) are scattered, rows come out in FIRST-TOUCH
+ * order, explicit zeros are kept, duplicates are summed in traversal order.  Cp[n+1] is filled; Ci/Cx (capacity
+ * nnzA + nnzB, the reference's allocation) receive Cp[n] entries. */
+int csp3_csc_add_ff_host(int64_t m, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
+                         const int32_t *Bp, const int32_t *Bi, const double *Bx, double alpha, double beta, int32_t *Cp,
+                         int32_t *Ci, double *Cx);
+
 /* ---- [[A, B], [C, D]]: Jacobian assembly ------------------------------------------------------------------- */
 /* Replaces csc_stack_4_by_4_ff, src/CSparse3/csc_numba.py:640-720 (caller pack_4_by_4, src/CSparse3/csc.py:588-606).
  * Argument order as in the reference: (m, n, indices, indptr[, data]) per block.  Column-wise concatenation, the
@@ -203,6 +211,12 @@ int csp3_lu_refactor_ws(const csp3_lu_symbolic *sym, int64_t batch, const double
                         int32_t *status, void *stream);
 int csp3_lu_solve_ws(const csp3_lu_symbolic *sym, int64_t batch, void *work, const double *b, double *x,
                      void *stream);
+
+/* Pivot-growth indicator of the factors csp3_lu_refactor_ws left in `work`: growth[batch] (device) = max |L(i,j)|,
+ * i > j.  The pivot sequence is frozen at the first factorisation (there |L| <= 1/tol); values that drift can make a
+ * frozen pivot tiny, which shows here long before `status` reports a zero pivot.  Callers
+ * compare it with a limit and re-analyse the flagged systems (csp3_lu_analyze on that system's values). */
+int csp3_lu_growth_ws(const csp3_lu_symbolic *sym, int64_t batch, const void *work, double *growth, void *stream);
 
 /* Host-buffer batched refactor+solve: chunks the batch, overlapping H2D copies, kernels and D2H copies on
  * internal streams.  Ax[batch, nnzA], b[batch, n], x[batch, n], status[batch] are HOST pointers (pinned

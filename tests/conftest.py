@@ -51,3 +51,8 @@ def sort_columns(n, Cp, Ci, Cx):
         Ci[s:e] = Ci[s:e][o]
         Cx[s:e] = Cx[s:e][o]
     return Ci, Cx
+
+
+@pytest.fixture(scope="session")
+def golden_helpers():
+    return dict(np.load(os.path.join(GOLDEN, "reference_helpers.npz")))

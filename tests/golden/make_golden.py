@@ -98,5 +98,62 @@ def main():
     print("wrote", os.listdir(HERE))
 
 
+def helpers():
+    """Round 2: the reference's add kernel (alpha / beta form), its cs_* helpers and the topology kernels."""
+    K = ref_kernels()
+    d = {}
+    S_ = sp.csc_matrix(sp.random(53, 53, density=0.06, random_state=8))
+    T_ = sp.csc_matrix(sp.random(53, 53, density=0.05, random_state=9))
+    d.update(pack("S", S_)); d.update(pack("T", T_))
+    # unsorted input with duplicates: the column-wise concatenation [S; S] folded back onto 53 rows
+    Dp = (2 * d["Sp"]).astype(np.int32)
+    Di = np.concatenate([np.r_[d["Si"][a:b], d["Si"][a:b][::-1]] for a, b in zip(d["Sp"][:-1], d["Sp"][1:])]).astype(np.int32)
+    Dx = np.concatenate([np.r_[d["Sx"][a:b], 0.5 * d["Sx"][a:b][::-1]] for a, b in zip(d["Sp"][:-1], d["Sp"][1:])])
+    d["Dp"], d["Di"], d["Dx"] = Dp, Di, Dx
+    for name, (Ap, Ai, Ax, Bp, Bi, Bx, al, be) in {
+            "add1": (d["Sp"], d["Si"], d["Sx"], d["Tp"], d["Ti"], d["Tx"], 2.5, -0.75),
+            "add2": (Dp, Di, Dx, d["Tp"], d["Ti"], d["Tx"], 1.0, 1.0),
+            "add3": (d["Sp"], d["Si"], d["Sx"], d["Sp"], d["Si"], d["Sx"], 1.0, -1.0)}.items():      # exact zeros are kept
+        Cm, Cn, Cp, Ci, Cx = K.csc_add_ff(53, 53, Ap, Ai, Ax, 53, 53, Bp, Bi, Bx, al, be)
+        d[name + "_p"], d[name + "_i"], d[name + "_x"] = Cp, np.array(Ci), np.array(Cx)
+    c = np.array([3, 0, 5, 1, 0, 7], dtype=np.int32); pcs = np.zeros(7, dtype=np.int32)
+    d["cumsum_in"] = c.copy()
+    d["cumsum_ret"] = np.array([K.csc_cumsum_i(pcs, c, 6)]); d["cumsum_p"], d["cumsum_c"] = pcs, c
+    m, n, Pp, Pi, Px, nzmax = K.csc_spalloc_f(4, 3, 0)
+    d["spalloc"] = np.array([m, n, len(Pp), len(Pi), len(Px), nzmax])
+    Ri, Rx, rz = K.csc_sprealloc_f(53, d["Sp"], d["Si"], d["Sx"], 0)
+    d["sprealloc0_i"], d["sprealloc0_x"], d["sprealloc0_nz"] = Ri, Rx, np.array([rz])
+    Ri, Rx, rz = K.csc_sprealloc_f(53, d["Sp"], d["Si"], d["Sx"], 40)
+    d["sprealloc40_i"], d["sprealloc40_x"] = Ri, Rx
+    w = np.zeros(53, dtype=np.int32); x = np.zeros(53); Ci = np.zeros(200, dtype=np.int32)
+    nz = K.csc_scatter_f(Dp, Di, Dx, 7, 2.0, w, x, 8, Ci, 0)
+    nz = K.csc_scatter_f(d["Tp"], d["Ti"], d["Tx"], 7, -1.5, w, x, 8, Ci, nz)
+    d["scatter_nz"], d["scatter_w"], d["scatter_x"], d["scatter_ci"] = np.array([nz]), w, x, Ci
+    # topology: islands of a graph with several components (symmetric adjacency in CSC), sub-matrices
+    rng = np.random.default_rng(5)
+    nn = 60
+    ei = rng.integers(0, nn, 45); ej = (ei + rng.integers(1, 4, 45)) % nn
+    keep = (ei // 12) == (ej // 12)                                   # edges only inside blocks of 12 nodes -> >= 5 islands
+    G = sp.coo_matrix((np.ones(keep.sum() * 2), (np.r_[ei[keep], ej[keep]], np.r_[ej[keep], ei[keep]])), shape=(nn, nn)).tocsc()
+    G.sum_duplicates()
+    d.update(pack("G", G))
+    isl = K.find_islands(nn, d["Gp"], d["Gi"])
+    d["islands_flat"] = np.array([v for isle in isl for v in isle], dtype=np.int64)
+    d["islands_len"] = np.array([len(isle) for isle in isl], dtype=np.int64)
+    rows = np.array([5, 2, 40, 41, 7, 3], dtype=np.int32); cols = np.array([9, 0, 33, 2], dtype=np.int32)
+    d["sub_rows"], d["sub_cols"] = rows, cols
+    nS = int(d["Sp"][-1])
+    for name, res in {"sub": K.csc_sub_matrix(53, nS, d["Sp"], d["Si"], d["Sx"], rows, cols),
+                      "subc": K.csc_sub_matrix_cols(53, nS, d["Sp"], d["Si"], d["Sx"], cols),
+                      "subr": K.csc_sub_matrix_rows(53, nS, d["Sp"], d["Si"], d["Sx"], rows)}.items():
+        d[name + "_n"], d[name + "_p"], d[name + "_i"], d[name + "_x"] = np.array([res[0]]), res[1], np.array(res[2]), np.array(res[3])
+    np.savez_compressed(os.path.join(HERE, "reference_helpers.npz"), **d)
+    print("wrote reference_helpers.npz")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "helpers":
+        helpers()
+    else:
+        main()
+        helpers()
