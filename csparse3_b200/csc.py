@@ -97,6 +97,8 @@ class CscMat:
         """Reference csc.py:348-423: matrix -> two-pass SpGEMM, 1-D array -> SpMV, 2-D array -> SpMM,
         scalar -> scaled copy."""
         if isinstance(other, CscMat):
+            if self.n != other.m:
+                raise ValueError("dimension mismatch: (%d, %d) * (%d, %d)" % (self.m, self.n, other.m, other.n))
             Cp = np.empty(other.n + 1, dtype=np.int32)
             sptools.csc_matmat_pass1(self.m, other.n, self.indptr, self.indices, other.indptr, other.indices, Cp)
             nnz = int(Cp[-1])
@@ -107,6 +109,8 @@ class CscMat:
             nnz = int(Cp[-1])
             return CscMat(m=self.m, n=other.n, indptr=Cp, indices=Ci[:nnz], data=Cx[:nnz])
         if isinstance(other, np.ndarray):
+            if other.shape[0] != self.n:
+                raise ValueError("dimension mismatch: (%d, %d) * %s" % (self.m, self.n, other.shape))
             if other.ndim == 1:
                 y = np.zeros(self.m, dtype=np.float64)
                 sptools.csc_matvec(self.m, self.n, self.indptr, self.indices, self.data, other, y)

@@ -181,6 +181,8 @@ class _SpTools:
         (Structural count, like pass 1 of SMMP: cancellations are not anticipated.)"""
         Ap, Ai, Bp, Bi = as_i32(Ap, "Ap"), as_i32(Ai, "Ai"), as_i32(Bp, "Bp"), as_i32(Bi, "Bi")
         An = len(Ap) - 1
+        if len(Bp) != n_col + 1 or (len(Bi) and int(Bi.max()) >= An) or (len(Ai) and int(Ai.max()) >= n_row):
+            raise ValueError("csc_matmat_pass1: inner dimensions do not match (A has %d columns)" % An)
         nnz = C.c_int64(0)
         rc = _lib.lib().csp3_spgemm_symbolic_host(n_row, An, ptr(Ap), ptr(Ai), An, n_col, ptr(Bp), ptr(Bi), ptr(Cp),
                                                   C.byref(nnz))
@@ -195,6 +197,8 @@ class _SpTools:
         Ap, Ai, Ax = as_i32(Ap, "Ap"), as_i32(Ai, "Ai"), as_f64(Ax, "Ax")
         Bp, Bi, Bx = as_i32(Bp, "Bp"), as_i32(Bi, "Bi"), as_f64(Bx, "Bx")
         An = len(Ap) - 1
+        if len(Bp) != n_col + 1 or (len(Bi) and int(Bi.max()) >= An) or (len(Ai) and int(Ai.max()) >= n_row):
+            raise ValueError("csc_matmat_pass2: inner dimensions do not match (A has %d columns)" % An)
         check(_lib.lib().csp3_spgemm_numeric_host(n_row, An, ptr(Ap), ptr(Ai), ptr(Ax), An, n_col, ptr(Bp), ptr(Bi),
                                                   ptr(Bx), ptr(Cp), ptr(Ci), ptr(Cx)), "csc_matmat_pass2")
         nnz = int(Cp[n_col])

@@ -199,6 +199,8 @@ int csp3_spmv_plan_create(int64_t m, int64_t n, const int32_t *Ap_dev, const int
     int rc = transpose_device(m, n, Ap_dev, Ai_dev, nullptr, nnz, P->d.rp, P->d.rc, nullptr, P->d.perm, st);
     if (rc == 0) rc = spmv_plan_pack(P->d, st);
     if (rc) { csp3_spmv_plan_destroy(P); return rc; }
+    // the plan may be used on any stream afterwards: its index arrays must be complete when this call returns
+    if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("spmv_plan_create: %s", cudaGetErrorString(cudaGetLastError())); csp3_spmv_plan_destroy(P); return CSP3_ERR_CUDA; }
     *plan = P;
     return 0;
 }
@@ -438,8 +440,14 @@ int csp3_lu_analyze(int64_t order, int64_t n, const int32_t *Ap, const int32_t *
     Sy->n = n; Sy->nnzA = Ap[n];
     Sy->Ap.assign(Ap, Ap + n + 1);
     Sy->Ai.assign(Ai, Ai + Ap[n]);
-    if (q_in) Sy->q.assign(q_in, q_in + n);
-    else Sy->q = amd_order(order, n, n, Ap, Ai);
+    if (q_in) {
+        Sy->q.assign(q_in, q_in + n);
+        std::vector<char> seen((size_t)n, 0);
+        for (i64 k = 0; k < n; ++k) {
+            if (q_in[k] < 0 || q_in[k] >= n || seen[(size_t)q_in[k]]) { set_error("lu_analyze: q is not a permutation of 0..n-1"); return CSP3_ERR_ARG; }
+            seen[(size_t)q_in[k]] = 1;
+        }
+    } else Sy->q = amd_order(order, n, n, Ap, Ai);
     const int st = lu_factor(n, Ap, Ai, Ax, Sy->q.data(), tol, Sy->F);
     if (st != 0) { set_error("lu_analyze: no non-zero pivot in step %d", st - 1); return st; }
     const char *why = "";
@@ -465,6 +473,20 @@ int csp3_lu_analyze_fixed(int64_t n, const int32_t *Ap, const int32_t *Ai, const
     F.Lp.assign(Lp, Lp + n + 1); F.Li.assign(Li, Li + Lp[n]);
     F.Up.assign(Up, Up + n + 1); F.Ui.assign(Ui, Ui + Up[n]);
     F.Lx.assign((size_t)Lp[n], 0.0); F.Ux.assign((size_t)Up[n], 0.0);
+    {   // the compiled device programs index memory with these arrays: check them before anything is built from them
+        auto is_perm = [&](const std::vector<i32> &p) {
+            std::vector<char> seen((size_t)n, 0);
+            for (i64 k = 0; k < n; ++k) { if (p[(size_t)k] < 0 || p[(size_t)k] >= n || seen[(size_t)p[(size_t)k]]) return false; seen[(size_t)p[(size_t)k]] = 1; }
+            return true;
+        };
+        if (!is_perm(Sy->q) || !is_perm(F.pinv)) { set_error("lu_analyze_fixed: q and pinv must be permutations of 0..n-1"); return CSP3_ERR_ARG; }
+        if (Lp[0] != 0 || Up[0] != 0 || Ap[0] != 0) { set_error("lu_analyze_fixed: column pointers must start at 0"); return CSP3_ERR_ARG; }
+        for (i64 k = 0; k < n; ++k)
+            if (Lp[k + 1] < Lp[k] || Up[k + 1] < Up[k] || Ap[k + 1] < Ap[k]) { set_error("lu_analyze_fixed: column pointers must be non-decreasing"); return CSP3_ERR_ARG; }
+        for (i64 p = 0; p < Lp[n]; ++p) if (Li[p] < 0 || Li[p] >= n) { set_error("lu_analyze_fixed: Li out of range"); return CSP3_ERR_ARG; }
+        for (i64 p = 0; p < Up[n]; ++p) if (Ui[p] < 0 || Ui[p] >= n) { set_error("lu_analyze_fixed: Ui out of range"); return CSP3_ERR_ARG; }
+        for (i64 p = 0; p < Ap[n]; ++p) if (Ai[p] < 0 || Ai[p] >= n) { set_error("lu_analyze_fixed: Ai out of range"); return CSP3_ERR_ARG; }
+    }
     for (i64 k = 0; k < n; ++k) {
         if (Lp[k + 1] <= Lp[k] || Li[Lp[k]] != k || Up[k + 1] <= Up[k] || Ui[Up[k + 1] - 1] != k) {
             set_error("lu_analyze_fixed: column %lld is not in cs_lu layout (L diagonal first, U diagonal last)", (long long)k);
@@ -614,8 +636,16 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
     char *arena = nullptr;
     if (cudaMalloc((void **)&arena, total ? total : 256) != cudaSuccess) { set_error("lu_upload: device allocation of %zu bytes failed", total); cudaGetLastError(); return CSP3_ERR_ALLOC; }
     for (auto &pc : pieces)
-        if (pc.bytes) CSP3_CUDA(cudaMemcpyAsync(arena + pc.off, pc.src, pc.bytes, cudaMemcpyHostToDevice, st));
-    CSP3_CUDA(cudaStreamSynchronize(st));
+        if (pc.bytes && cudaMemcpyAsync(arena + pc.off, pc.src, pc.bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            set_error("lu_upload: copy failed (%s)", cudaGetErrorString(cudaGetLastError()));
+            cudaFree(arena);
+            return CSP3_ERR_CUDA;
+        }
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error("lu_upload: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaFree(arena);
+        return CSP3_ERR_CUDA;
+    }
     auto at = [&](size_t idx) { return (const void *)(arena + pieces[idx].off); };
     D.arena = arena; D.arena_bytes = total;
     D.n = (i32)sym->n; D.nnzA = (i32)sym->nnzA; D.lnz = (i32)F.Li.size(); D.unz = (i32)F.Ui.size();
@@ -753,9 +783,12 @@ int csp3_lu_refactor_solve_host(csp3_lu_symbolic *sym, int64_t batch, const doub
     if (int rc = csp3_lu_upload(sym, nullptr)) return rc;
     int devid = 0;
     CSP3_CUDA(cudaGetDevice(&devid));
+    // The staging buffers and streams belong to the handle: calls on one handle are serialised (two host threads may
+    // share a symbolic object; concurrent batches need one handle per thread or the device-pointer entry points).
+    std::lock_guard<std::mutex> lock(sym->mu);
     const DevSchedule &D = sym->dev[devid];
     auto &G = sym->stage[devid];
-    const i64 n = D.n, nnzA = D.nnzA, lnz = D.lnz, unz = D.unz;
+    const i64 n = D.n, nnzA = D.nnzA;
     if (!G.ready) {
         // The kernels are latency-bound: a chunk costs about the same time whether it holds 500 or 5,000
         // systems, so chunks are as large as ~512 MB of values allows (kernels of different chunks overlap on
@@ -764,30 +797,46 @@ int csp3_lu_refactor_solve_host(csp3_lu_symbolic *sym, int64_t batch, const doub
         chunk = std::max<i64>(256, std::min<i64>(chunk, 4096));
         chunk = (chunk + 31) & ~31ll;
         G.chunk = chunk;
-        for (int s = 0; s < 3; ++s) {
-            CSP3_CUDA(cudaStreamCreateWithFlags(&G.st[s], cudaStreamNonBlocking));
-            CSP3_CUDA(cudaMalloc((void **)&G.Ax[s], (size_t)chunk * nnzA * 8 + 16));
-            CSP3_CUDA(cudaMalloc((void **)&G.b[s], (size_t)chunk * n * 8 + 16));
-            CSP3_CUDA(cudaMalloc((void **)&G.x[s], (size_t)chunk * n * 8 + 16));
-            CSP3_CUDA(cudaMalloc((void **)&G.Lx[s], (size_t)csp3_lu_workspace_bytes(sym, chunk)));   // factor workspace
-            CSP3_CUDA(cudaMalloc((void **)&G.status[s], (size_t)chunk * 4 + 16));
+        bool ok = true;
+        for (int s = 0; s < 3 && ok; ++s) {
+            ok = cudaStreamCreateWithFlags(&G.st[s], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaMalloc((void **)&G.Ax[s], (size_t)chunk * nnzA * 8 + 16) == cudaSuccess &&
+                 cudaMalloc((void **)&G.b[s], (size_t)chunk * n * 8 + 16) == cudaSuccess &&
+                 cudaMalloc((void **)&G.x[s], (size_t)chunk * n * 8 + 16) == cudaSuccess &&
+                 cudaMalloc((void **)&G.Lx[s], (size_t)csp3_lu_workspace_bytes(sym, chunk)) == cudaSuccess &&   // factor workspace
+                 cudaMalloc((void **)&G.status[s], (size_t)chunk * 4 + 16) == cudaSuccess;
+        }
+        if (!ok) {
+            set_error("lu_refactor_solve_host: staging allocation failed (%s)", cudaGetErrorString(cudaGetLastError()));
+            free_stage(G);                                    // nothing half-built is kept
+            return CSP3_ERR_ALLOC;
         }
         G.ready = true;
     }
-    (void)lnz; (void)unz;
-    int slot = 0;
-    for (i64 s0 = 0; s0 < batch; s0 += G.chunk, slot = (slot + 1) % 3) {
+    int rc = 0, slot = 0;
+    for (i64 s0 = 0; s0 < batch && rc == 0; s0 += G.chunk, slot = (slot + 1) % 3) {
         const i64 cnt = std::min<i64>(G.chunk, batch - s0);
         cudaStream_t st = G.st[slot];
-        CSP3_CUDA(cudaMemcpyAsync(G.Ax[slot], Ax + s0 * nnzA, (size_t)cnt * nnzA * 8, cudaMemcpyHostToDevice, st));
-        CSP3_CUDA(cudaMemcpyAsync(G.b[slot], b + s0 * n, (size_t)cnt * n * 8, cudaMemcpyHostToDevice, st));
-        if (int rc = csp3_lu_refactor_ws(sym, cnt, G.Ax[slot], G.Lx[slot], G.status[slot], st)) return rc;
-        if (int rc = csp3_lu_solve_ws(sym, cnt, G.Lx[slot], G.b[slot], G.x[slot], st)) return rc;
-        CSP3_CUDA(cudaMemcpyAsync(x + s0 * n, G.x[slot], (size_t)cnt * n * 8, cudaMemcpyDeviceToHost, st));
-        if (status) CSP3_CUDA(cudaMemcpyAsync(status + s0, G.status[slot], (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+        auto cp = [&](void *d, const void *h, size_t bytes, cudaMemcpyKind k) {
+            if (rc == 0 && cudaMemcpyAsync(d, h, bytes, k, st) != cudaSuccess) {
+                set_error("lu_refactor_solve_host: copy failed (%s)", cudaGetErrorString(cudaGetLastError()));
+                rc = CSP3_ERR_CUDA;
+            }
+        };
+        cp(G.Ax[slot], Ax + s0 * nnzA, (size_t)cnt * nnzA * 8, cudaMemcpyHostToDevice);
+        cp(G.b[slot], b + s0 * n, (size_t)cnt * n * 8, cudaMemcpyHostToDevice);
+        if (rc == 0) rc = csp3_lu_refactor_ws(sym, cnt, G.Ax[slot], G.Lx[slot], G.status[slot], st);
+        if (rc == 0) rc = csp3_lu_solve_ws(sym, cnt, G.Lx[slot], G.b[slot], G.x[slot], st);
+        cp(x + s0 * n, G.x[slot], (size_t)cnt * n * 8, cudaMemcpyDeviceToHost);
+        if (status) cp(status + s0, G.status[slot], (size_t)cnt * 4, cudaMemcpyDeviceToHost);
     }
-    for (int s = 0; s < 3; ++s) CSP3_CUDA(cudaStreamSynchronize(G.st[s]));
-    return 0;
+    // also after an error: nothing queued on the three streams may still target the caller's buffers when we return
+    for (int s = 0; s < 3; ++s)
+        if (cudaStreamSynchronize(G.st[s]) != cudaSuccess && rc == 0) {
+            set_error("lu_refactor_solve_host: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = CSP3_ERR_CUDA;
+        }
+    return rc;
 }
 
 int csp3_lu_refactor_host(csp3_lu_symbolic *sym, int64_t batch, const double *Ax, double *Lx, double *Ux,

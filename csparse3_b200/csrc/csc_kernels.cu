@@ -182,15 +182,18 @@ __global__ void k_expand_cols(int n, const i32 *__restrict__ Ap, i32 *col)
         for (int p = __ldg(Ap + j); p < __ldg(Ap + j + 1); ++p) col[p] = j;
 }
 
-__global__ void k_row_emit(int m, int n, const i32 *__restrict__ Ap, const double *__restrict__ Ax,
-                           const i32 *__restrict__ ptr, const i32 *__restrict__ bucket, const i32 *__restrict__ col,
-                           i32 *perm, i32 *Ci, double *Cx)
+constexpr int kRowThreadMax = 48;       // rows up to this length are rank-sorted by one thread, longer ones by a CTA
+
+// short rows (a handful of entries): one thread per row instead of one warp per row; a longer row is appended to
+// `longrows` (count in longrows[0]) and left to k_row_emit_long, so one dense row never serialises in a thread
+__global__ void k_row_emit_thread(int m, int n, const i32 *__restrict__ Ap, const double *__restrict__ Ax,
+                                  const i32 *__restrict__ ptr, const i32 *__restrict__ bucket, const i32 *__restrict__ col,
+                                  i32 *perm, i32 *Ci, double *Cx, i32 *longrows)
 {
-    const int lane = threadIdx.x & 31;
-    const int wpb = blockDim.x >> 5;
-    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < m; r += gridDim.x * wpb) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
         const int beg = __ldg(ptr + r), len = __ldg(ptr + r + 1) - beg;
-        for (int t = lane; t < len; t += 32) {
+        if (len > kRowThreadMax) { longrows[1 + atomicAdd(longrows, 1)] = r; continue; }
+        for (int t = 0; t < len; ++t) {
             const int p = __ldg(bucket + beg + t);
             int rank = 0;
             for (int u = 0; u < len; ++u) rank += (__ldg(bucket + beg + u) < p);
@@ -201,20 +204,51 @@ __global__ void k_row_emit(int m, int n, const i32 *__restrict__ Ap, const doubl
     }
 }
 
-// short rows (a handful of entries): one thread per row instead of one warp per row
-__global__ void k_row_emit_thread(int m, int n, const i32 *__restrict__ Ap, const double *__restrict__ Ax,
-                                  const i32 *__restrict__ ptr, const i32 *__restrict__ bucket, const i32 *__restrict__ col,
-                                  i32 *perm, i32 *Ci, double *Cx)
+// long rows of the worklist: one CTA per row.  Up to kLongSort entries are sorted in shared memory (bitonic, keys are
+// the distinct source entry ids); longer rows fall back to ranking with the whole CTA (len^2 / 1024 steps per thread).
+constexpr int kLongSort = 4096;
+__global__ void __launch_bounds__(1024)
+k_row_emit_long(int n, const i32 *__restrict__ Ap, const double *__restrict__ Ax, const i32 *__restrict__ ptr,
+                const i32 *__restrict__ bucket, const i32 *__restrict__ col, i32 *perm, i32 *Ci, double *Cx,
+                const i32 *__restrict__ longrows)
 {
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
+    __shared__ i32 key[kLongSort];
+    const int nlong = longrows[0];
+    for (int w = blockIdx.x; w < nlong; w += gridDim.x) {
+        const int r = longrows[1 + w];
         const int beg = __ldg(ptr + r), len = __ldg(ptr + r + 1) - beg;
-        for (int t = 0; t < len; ++t) {
-            const int p = __ldg(bucket + beg + t);
-            int rank = 0;
-            for (int u = 0; u < len; ++u) rank += (__ldg(bucket + beg + u) < p);
-            if (perm) perm[beg + rank] = p;
-            if (Ci) Ci[beg + rank] = col ? __ldg(col + p) : column_of(Ap, n, p);
-            if (Cx) Cx[beg + rank] = __ldg(Ax + p);
+        if (len <= kLongSort) {
+            int pw = 1;
+            while (pw < len) pw <<= 1;
+            for (int t = threadIdx.x; t < pw; t += blockDim.x) key[t] = t < len ? __ldg(bucket + beg + t) : INT32_MAX;
+            __syncthreads();
+            for (int k = 2; k <= pw; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = threadIdx.x; t < pw; t += blockDim.x) {
+                        const int u = t ^ j;
+                        if (u > t) {
+                            const i32 a = key[t], b = key[u];
+                            if (((t & k) == 0) ? (a > b) : (a < b)) { key[t] = b; key[u] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            for (int t = threadIdx.x; t < len; t += blockDim.x) {
+                const int p = key[t];
+                if (perm) perm[beg + t] = p;
+                if (Ci) Ci[beg + t] = col ? __ldg(col + p) : column_of(Ap, n, p);
+                if (Cx) Cx[beg + t] = __ldg(Ax + p);
+            }
+            __syncthreads();
+        } else {
+            for (int t = threadIdx.x; t < len; t += blockDim.x) {
+                const int p = __ldg(bucket + beg + t);
+                int rank = 0;
+                for (int u = 0; u < len; ++u) rank += (__ldg(bucket + beg + u) < p);
+                if (perm) perm[beg + rank] = p;
+                if (Ci) Ci[beg + rank] = col ? __ldg(col + p) : column_of(Ap, n, p);
+                if (Cx) Cx[beg + rank] = __ldg(Ax + p);
+            }
         }
     }
 }
@@ -413,6 +447,29 @@ __device__ void spgemm_column(int j, int tid, int nthr, const i32 *__restrict__ 
         __syncwarp();
         return;
     }
+    if (BLOCK && compact != nullptr) {
+        // CTA mode: occupied keys are compacted into the CTA's global scratch (any order: ranks do not depend on it),
+        // so ranking costs occupied x occupied / threads comparisons instead of occupied x slots
+        __shared__ int s_occ;
+        if (tid == 0) s_occ = 0;
+        __syncthreads();
+        for (int s = tid; s < slots; s += nthr) {
+            const int row = keys[s];
+            if (row >= 0) compact[atomicAdd(&s_occ, 1)] = row;
+        }
+        __syncthreads();
+        const int occ = s_occ;
+        for (int s = tid; s < slots; s += nthr) {
+            const int row = keys[s];
+            if (row < 0) continue;
+            int rank = 0;
+            for (int u = 0; u < occ; ++u) rank += (compact[u] < row);
+            Ci[base + rank] = row;
+            Cx[base + rank] = vals[s];
+        }
+        __syncthreads();
+        return;
+    }
     for (int s = tid; s < slots; s += nthr) {
         const int row = keys[s];
         if (row < 0) continue;
@@ -477,18 +534,36 @@ k_spgemm_small_all(int Bn, i64 Am, const i32 *__restrict__ ub, const i32 *__rest
 
 template <bool NUMERIC>
 __global__ void __launch_bounds__(kThreads)
-k_spgemm_big_all(int Bn, i64 Am, const i32 *__restrict__ ub, const i64 *__restrict__ tab_off, const i32 *__restrict__ Ap,
+k_spgemm_big_all(int Bn, i64 Am, const i32 *__restrict__ ub, i64 tab_slots, const i32 *__restrict__ Ap,
                  const i32 *__restrict__ Ai, const double *__restrict__ Ax, const i32 *__restrict__ Bp, const i32 *__restrict__ Bi,
-                 const double *__restrict__ Bx, i32 *tab_keys, double *tab_vals, i32 *count_out, const i32 *__restrict__ Cp,
-                 i32 *Ci, double *Cx)
+                 const double *__restrict__ Bx, i32 *tab_keys, double *tab_vals, i32 *tab_compact, i32 *count_out,
+                 const i32 *__restrict__ Cp, i32 *Ci, double *Cx)
 {
+    // every resident CTA owns ONE table sized for the largest big column and reuses it for all its columns: the
+    // memory is O(CTAs x largest column), not O(sum over the big columns)
+    const i64 off = (i64)blockIdx.x * tab_slots;
     for (int j = blockIdx.x; j < Bn; j += gridDim.x) {
         const i64 slots = spgemm_slots(__ldg(ub + j), Am);                  // uniform over the CTA
         if (slots <= kSmallSlots) continue;
-        const i64 off = tab_off[j];
         spgemm_column<NUMERIC, true>(j, threadIdx.x, blockDim.x, Ap, Ai, Ax, Bp, Bi, Bx, tab_keys + off,
-                                     NUMERIC ? tab_vals + off : nullptr, (unsigned)slots - 1u, count_out, Cp, Ci, Cx);
+                                     NUMERIC ? tab_vals + off : nullptr, (unsigned)slots - 1u, count_out, Cp, Ci, Cx,
+                                     NUMERIC ? tab_compact + off / 2 : nullptr);
     }
+}
+
+// largest value of v[0..n) (single CTA; n is the number of columns)
+__global__ void k_max64(int n, const i64 *__restrict__ v, i64 *out)
+{
+    __shared__ i64 part[1024];
+    i64 m = 0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) m = max(m, v[j]);
+    part[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) part[threadIdx.x] = max(part[threadIdx.x], part[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = part[0];
 }
 
 // ---- C = A + sign*B (sparsetools csr_binop_csr semantics: duplicates summed per operand, exact zeros dropped) ----
@@ -643,12 +718,15 @@ int transpose_device(i64 m, i64 n, const i32 *Ap, const i32 *Ai, const double *A
         const bool expand = Ci != nullptr && col.alloc((size_t)nnz * 4) == 0;
         if (expand) k_expand_cols<<<grid_for(n, kThreads), kThreads, 0, st>>>((int)n, Ap, col.as<i32>());
         k_bucket_fill<<<grid_for(nnz, kThreads), kThreads, 0, st>>>(nnz, Ai, cursor.as<i32>(), bucket.as<i32>());
-        if ((i64)nnz <= 12 * m)
-            k_row_emit_thread<<<grid_for(m, kThreads), kThreads, 0, st>>>((int)m, (int)n, Ap, Ax, Cp, bucket.as<i32>(),
-                                                                          expand ? col.as<i32>() : nullptr, perm, Ci, Cx);
-        else
-            k_row_emit<<<grid_for(m, kThreads / 32), kThreads, 0, st>>>((int)m, (int)n, Ap, Ax, Cp, bucket.as<i32>(),
-                                                                         expand ? col.as<i32>() : nullptr, perm, Ci, Cx);
+        // the emit path is chosen per ROW (a matrix with a few entries per row on average may still hold a dense row):
+        // rows up to kRowThreadMax entries by one thread each, the others through a worklist by one CTA each
+        DevBuf longrows(st);
+        if (longrows.alloc((size_t)(m + 1) * 4)) { set_error("device alloc failed"); return -3; }
+        CSP3_CUDA(cudaMemsetAsync(longrows.p, 0, 4, st));
+        k_row_emit_thread<<<grid_for(m, kThreads), kThreads, 0, st>>>((int)m, (int)n, Ap, Ax, Cp, bucket.as<i32>(),
+                                                                      expand ? col.as<i32>() : nullptr, perm, Ci, Cx, longrows.as<i32>());
+        k_row_emit_long<<<kNumSMs, 1024, 0, st>>>((int)n, Ap, Ax, Cp, bucket.as<i32>(), expand ? col.as<i32>() : nullptr, perm, Ci, Cx,
+                                                  longrows.as<i32>());
     }
     CSP3_CUDA(cudaGetLastError());
     return 0;
@@ -708,15 +786,18 @@ int spgemm_device(bool numeric, i64 Am, i64 An, const i32 *Ap, const i32 *Ai, co
     if (Bn == 0) { if (!numeric) { CSP3_CUDA(cudaMemsetAsync(Cp, 0, 4, st)); if (nnz_out) *nnz_out = 0; } return 0; }
     // Planning stays on the device (one 8-byte read-back for the size of the global hash tables): candidate
     // products per column -> table size per column -> offsets of the big columns' tables by a prefix sum.
-    DevBuf ub(st), boff(st), tkeys(st), tvals(st), cnt(st);
+    DevBuf ub(st), boff(st), tkeys(st), tvals(st), tcomp(st), cnt(st);
     if (ub.alloc((size_t)Bn * 4) || boff.alloc((size_t)(Bn + 1) * 8)) { set_error("device alloc failed"); return -3; }
     k_spgemm_ub<<<grid_for(Bn, kThreads), kThreads, 0, st>>>((int)Bn, Ap, Bp, Bi, ub.as<i32>());
     k_spgemm_bigslots<<<grid_for(Bn, kThreads), kThreads, 0, st>>>((int)Bn, Am, ub.as<i32>(), boff.as<i64>());
-    if (scan_i64((int)Bn, boff.as<i64>(), st)) { set_error("device alloc failed"); return -3; }
-    i64 tab_total = 0;
+    k_max64<<<1, 1024, 0, st>>>((int)Bn, boff.as<i64>(), boff.as<i64>() + Bn);
+    i64 tab_total = 0;                                   // slots of the largest big column (0: no big column)
     CSP3_CUDA(cudaMemcpyAsync(&tab_total, boff.as<i64>() + Bn, 8, cudaMemcpyDeviceToHost, st));
     CSP3_CUDA(cudaStreamSynchronize(st));
-    if (tab_total > 0 && (tkeys.alloc((size_t)tab_total * 4) || (numeric && tvals.alloc((size_t)tab_total * 8)))) {
+    // one table per resident CTA; the grid shrinks when the largest column is huge (at most ~1 GiB of tables)
+    const int big_grid = tab_total > 0 ? (int)std::max<i64>(1, std::min<i64>(std::min<i64>(Bn, kNumSMs * 4), (1ll << 30) / (tab_total * 14))) : 0;
+    if (tab_total > 0 && (tkeys.alloc((size_t)tab_total * big_grid * 4) ||
+                          (numeric && (tvals.alloc((size_t)tab_total * big_grid * 8) || tcomp.alloc((size_t)tab_total * big_grid * 2))))) {
         set_error("spgemm: device alloc failed");
         return -3;
     }
@@ -738,9 +819,9 @@ int spgemm_device(bool numeric, i64 Am, i64 An, const i32 *Ap, const i32 *Ai, co
         }
     }
     if (tab_total > 0) {
-        const int g = (int)std::min<i64>(Bn, kNumSMs * 4);
-        if (numeric) k_spgemm_big_all<true><<<g, kThreads, 0, st>>>((int)Bn, Am, ub.as<i32>(), boff.as<i64>(), Ap, Ai, Ax, Bp, Bi, Bx, tkeys.as<i32>(), tvals.as<double>(), nullptr, Cp, Ci, Cx);
-        else k_spgemm_big_all<false><<<g, kThreads, 0, st>>>((int)Bn, Am, ub.as<i32>(), boff.as<i64>(), Ap, Ai, Ax, Bp, Bi, Bx, tkeys.as<i32>(), nullptr, count, nullptr, nullptr, nullptr);
+        const int g = big_grid;
+        if (numeric) k_spgemm_big_all<true><<<g, kThreads, 0, st>>>((int)Bn, Am, ub.as<i32>(), tab_total, Ap, Ai, Ax, Bp, Bi, Bx, tkeys.as<i32>(), tvals.as<double>(), tcomp.as<i32>(), nullptr, Cp, Ci, Cx);
+        else k_spgemm_big_all<false><<<g, kThreads, 0, st>>>((int)Bn, Am, ub.as<i32>(), tab_total, Ap, Ai, Ax, Bp, Bi, Bx, tkeys.as<i32>(), nullptr, nullptr, count, nullptr, nullptr, nullptr);
     }
     CSP3_CUDA(cudaGetLastError());
     if (!numeric) {

@@ -142,3 +142,30 @@ def test_panel_refactor_kernel_parity(env):
         "print('ok')\n") % (ROOT, "CSP3_PANEL_FMA" in env)
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_transpose_with_dense_rows_and_spgemm_with_big_columns():
+    """Shapes the per-row / per-column path selection exists for: a matrix that is sparse on average
+    but holds dense rows (transposition: worklist + CTA sort, 3 length classes), and a product whose columns all
+    exceed the shared-memory hash table (one reusable global table per CTA)."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(9)
+    m, n = 30000, 25000
+    A = sp.random(m, n, density=2e-4, random_state=4, format="lil")
+    A[7, :] = rng.standard_normal(n)                         # 25,000 entries: beyond the shared-memory sort
+    cols = rng.choice(n, 3000, replace=False); A[11, cols] = 1.5          # CTA bitonic sort
+    cols = rng.choice(n, 200, replace=False); A[13, cols] = -2.0          # just above the one-thread limit
+    A = sp.csc_matrix(A); A.sort_indices()
+    Ap, Ai, Ax = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()
+    T = B.csc_transpose(m, n, Ap, Ai, Ax)
+    o = orc.csc_transpose(m, n, Ap, Ai, Ax)
+    assert np.array_equal(T[2], o[2]) and np.array_equal(T[3], o[3]) and np.array_equal(T[4], o[4])
+    k = 3000
+    M = sp.csc_matrix(sp.random(k, k, density=0.012, random_state=6) + sp.eye(k)); M.sort_indices()   # ~37 entries per column
+    Mp, Mi, Mx = M.indptr.astype(np.int32), M.indices.astype(np.int32), M.data.copy()
+    assert np.diff(Mp).mean() ** 2 > 512
+    Cm, Cn, Cp, Ci, Cx, nnz = B.csc_multiply_ff(k, k, Mp, Mi, Mx, k, k, Mp, Mi, Mx)
+    Om, On, Op, Oi, Ox, onnz = orc.csc_multiply_ff(k, k, Mp, Mi, Mx, k, k, Mp, Mi, Mx)
+    assert nnz == onnz and np.array_equal(Cp, Op)
+    order = np.lexsort((Oi, np.repeat(np.arange(k), np.diff(Op))))
+    assert np.array_equal(Ci, Oi[order]) and np.array_equal(Cx, Ox[order])
