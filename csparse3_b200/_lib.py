@@ -69,6 +69,10 @@ SIGNATURES = {
     "csp3_lu_refactor_host": [vp, i64, vp, vp, vp, vp],
     "csp3_lu_solve_host": [vp, i64, vp, vp, vp, vp],
     "csp3_csc_lusol_host": [i64, i64, vp, vp, vp, vp, f64],
+    "csp3_find_islands_host": [i64, vp, vp, vp, vp, C.POINTER(i64)],
+    "csp3_islands_batched": [i64, vp, vp, i64, vp, vp, vp, vp, vp],
+    "csp3_islands_batched_host": [i64, vp, vp, i64, vp, vp, vp, vp],
+    "csp3_csc_sub_matrix_host": [i64, i64, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, C.POINTER(i64)],
     "csp3_nr_create": [i64, i64, vp, vp, vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, vp, vp, C.POINTER(vp)],
     "csp3_nr_destroy": [vp],
     "csp3_nr_workspace_bytes": [vp, i64],

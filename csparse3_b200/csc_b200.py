@@ -26,7 +26,7 @@ __all__ = [
     "csc_add_ff", "csc_scatter_f", "csc_scatter_ff", "csc_spalloc_f", "csc_sprealloc_f", "ialloc", "xalloc",
     "csc_amd", "csc_etree", "csc_post", "csc_lu", "csc_lu_refactor", "csc_lu_solve", "csc_lusol",
     "csc_to_dense", "csc_diagonal", "csc_diagonal_from_array", "csc_stack_4_by_4_ff", "csc_sub_matrix",
-    "csc_sub_matrix_cols", "csc_sub_matrix_rows", "csc_norm", "find_islands", "coo_to_csc",
+    "csc_sub_matrix_cols", "csc_sub_matrix_rows", "csc_norm", "find_islands", "find_islands_batched", "coo_to_csc",
 ]
 
 
@@ -338,34 +338,39 @@ def csc_stack_4_by_4_ff(am, an, Ai, Ap, Ax, bm, bn, Bi, Bp, Bx, cm, cn, Ci, Cp, 
     return am + cm, an + bn, indices, indptr, data
 
 
+def _sub_matrix(Am, An, Ap, Ai, Ax, rows, cols):
+    Ap, Ai, Ax = as_i32(Ap, "Ap"), as_i32(Ai, "Ai"), as_f64(Ax, "Ax")
+    rows = None if rows is None else np.ascontiguousarray(rows, dtype=np.int32)
+    cols = None if cols is None else np.ascontiguousarray(cols, dtype=np.int32)
+    nc = An if cols is None else len(cols)
+    nz = int(Ap[An])
+    Bp = np.zeros(nc + 1, dtype=np.int32)
+    Bi = np.empty(max(nz, 1), dtype=np.int32)
+    Bx = np.empty(max(nz, 1), dtype=np.float64)
+    nnz = C.c_int64(0)
+    check(_lib.lib().csp3_csc_sub_matrix_host(Am, An, ptr(Ap), ptr(Ai), ptr(Ax), 0 if rows is None else len(rows), ptr(rows),
+                                              0 if cols is None else len(cols), ptr(cols), ptr(Bp), ptr(Bi), ptr(Bx),
+                                              C.byref(nnz)), "csc_sub_matrix")
+    n = int(nnz.value)
+    return n, Bp, Bi[:n], Bx[:n]
+
+
 def csc_sub_matrix_cols(Am, Anz, Ap, Ai, Ax, cols):
-    """csc_numba.py:505-537 -> (n, Bp, Bi, Bx)"""
-    cols = np.asarray(cols)
-    cnt = np.asarray(Ap)[cols + 1] - np.asarray(Ap)[cols]
-    Bp = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
-    src = np.concatenate([np.arange(Ap[c], Ap[c + 1]) for c in cols]) if len(cols) else np.zeros(0, dtype=np.int64)
-    src = src.astype(np.int64)
-    return int(Bp[-1]), Bp, np.asarray(Ai)[src].astype(np.int32), np.asarray(Ax)[src].astype(np.float64)
+    """Selected columns, all rows -> (n, Bp, Bi, Bx).  csc_numba.py:505-537; on the device (topo_kernels.cu)."""
+    return _sub_matrix(Am, len(Ap) - 1, Ap, Ai, Ax, None, cols)
 
 
 def csc_sub_matrix(Am, Anz, Ap, Ai, Ax, rows, cols):
-    """csc_numba.py:464-502 -> (n, Bp, Bi, Bx); rows are renumbered by their position in `rows`."""
-    Bp = [0]; Bi = []; Bx = []
-    for j in cols:
-        i = 0
-        for r in rows:
-            for k in range(Ap[j], Ap[j + 1]):
-                if Ai[k] == r:
-                    Bx.append(Ax[k]); Bi.append(i); i += 1
-            if i == 0:
-                i += 1
-        Bp.append(len(Bx))
-    return len(Bx), np.array(Bp, dtype=np.int32), np.array(Bi, dtype=np.int32), np.array(Bx, dtype=np.float64)
+    """Arbitrary sub-matrix -> (n, Bp, Bi, Bx).  csc_numba.py:464-502: entries ordered by the position of their row in
+    `rows`, numbered by the reference's running counter; on the device (topo_kernels.cu).  `rows` must not repeat."""
+    return _sub_matrix(Am, len(Ap) - 1, Ap, Ai, Ax, rows, cols)
 
 
 def csc_sub_matrix_rows(An, Anz, Ap, Ai, Ax, rows):
-    """csc_numba.py:541-578 -> (n, Bp, Bi, Bx)"""
-    return csc_sub_matrix(0, Anz, Ap, Ai, Ax, rows, range(An))
+    """Selected rows, all columns -> (n, Bp, Bi, Bx).  csc_numba.py:541-578; on the device."""
+    Ai = as_i32(Ai, "Ai")
+    Am = max(int(Ai.max()) + 1 if len(Ai) else 0, int(np.max(rows)) + 1 if len(rows) else 0)
+    return _sub_matrix(Am, An, Ap, Ai, Ax, rows, None)
 
 
 def csc_norm(n, Ap, Ax):
@@ -378,25 +383,32 @@ def csc_norm(n, Ap, Ax):
 
 
 def find_islands(node_number, indptr, indices):
-    """Connected components in the reference's visiting order.  csc_numba.py:743-808."""
-    visited = np.zeros(node_number, dtype=bool)
-    islands = []
-    for node in range(node_number):
-        if visited[node]:
-            continue
-        island = []
-        stack = [node]
-        while stack:
-            v = stack.pop(0)
-            if not visited[v]:
-                visited[v] = True
-                island.append(v)
-                for i in range(indptr[v], indptr[v + 1]):
-                    k = indices[i]
-                    if not visited[k]:
-                        stack.append(k)
-        islands.append(island)
-    return islands
+    """Islands of a graph -> list of lists of node ids, in the reference's order (islands by smallest node, nodes in
+    the order of its front-popped traversal).  csc_numba.py:743-808; on the device (topo_kernels.cu: hook + pointer
+    jumping for the components, then a level-synchronous breadth-first numbering)."""
+    indptr, indices = as_i32(indptr, "indptr"), as_i32(indices, "indices")
+    n = int(node_number)
+    order = np.empty(max(n, 1), dtype=np.int32)
+    iptr = np.zeros(n + 1, dtype=np.int32)
+    cnt = C.c_int64(0)
+    check(_lib.lib().csp3_find_islands_host(n, ptr(indptr), ptr(indices), ptr(order), ptr(iptr), C.byref(cnt)), "find_islands")
+    return [order[iptr[k]:iptr[k + 1]].tolist() for k in range(int(cnt.value))]
+
+
+def find_islands_batched(node_number, indptr, indices, out_from=None, out_to=None, batch=None):
+    """The N-1 form of find_islands: case c is the graph without the edge (out_from[c], out_to[c]) (-1: nothing removed).
+    -> (label[batch, n], n_islands[batch]); label = smallest node id of the node's island.  One CTA per case."""
+    indptr, indices = as_i32(indptr, "indptr"), as_i32(indices, "indices")
+    n = int(node_number)
+    if out_from is not None:
+        out_from, out_to = as_i32(out_from, "out_from"), as_i32(out_to, "out_to")
+        batch = len(out_from)
+    batch = 1 if batch is None else int(batch)
+    label = np.empty((batch, n), dtype=np.int32)
+    cnt = np.empty(batch, dtype=np.int32)
+    check(_lib.lib().csp3_islands_batched_host(n, ptr(indptr), ptr(indices), batch, ptr(out_from), ptr(out_to), ptr(label), ptr(cnt)),
+          "find_islands_batched")
+    return label, cnt
 
 
 def coo_to_csc(m, n, Ti, Tj, Tx, nz):

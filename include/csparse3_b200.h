@@ -235,6 +235,31 @@ int csp3_lu_solve_host(csp3_lu_symbolic *sym, int64_t batch, const double *Lx, c
 int csp3_csc_lusol_host(int64_t order, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
                         double *b, double tol);
 
+/* ---- topology operations on the device ------------------------------------------- */
+/* Replaces find_islands(node_number, indptr, indices), src/CSparse3/csc_numba.py:743-808 (caller CscMat.islands,
+ * csc.py:515-521): the islands of an undirected graph given as a symmetric adjacency pattern.  Output in the
+ * reference's order: islands by ascending smallest node, nodes inside an island in the order of its traversal
+ * (first appearance in its front-popped list = breadth-first from the smallest node, neighbours in adjacency order).
+ * order[n] = node ids, island k = order[island_ptr[k] .. island_ptr[k+1]); island_ptr has room for n + 1 entries. */
+int csp3_find_islands_host(int64_t n, const int32_t *indptr, const int32_t *indices, int32_t *order, int32_t *island_ptr,
+                           int64_t *n_islands);
+/* The N-1 form: `batch` cases share the adjacency pattern, case c has the edge between nodes out_from[c] and out_to[c]
+ * removed (both NULL, or -1: nothing removed).  label[batch, n] = smallest node id of the node's island (equal labels
+ * <=> same island; islands sorted by label are the reference's island order), islands[batch] = number of islands
+ * (> 1 for an outage that splits the grid: a bridge).  One CTA per case.  DEVICE pointers, stream-ordered. */
+int csp3_islands_batched(int64_t n, const int32_t *indptr, const int32_t *indices, int64_t batch, const int32_t *out_from,
+                         const int32_t *out_to, int32_t *label, int32_t *islands, void *stream);
+int csp3_islands_batched_host(int64_t n, const int32_t *indptr, const int32_t *indices, int64_t batch, const int32_t *out_from,
+                              const int32_t *out_to, int32_t *label, int32_t *islands);
+/* Replaces csc_sub_matrix / csc_sub_matrix_cols / csc_sub_matrix_rows, src/CSparse3/csc_numba.py:463-578 (callers
+ * CscMat.__getitem__, csc.py:150-292).  rows == NULL: every row, original row indices (the _cols kernel); cols == NULL:
+ * every column (the _rows kernel).  With `rows` the entries of a column come out ordered by the position of their row
+ * in `rows` and are numbered by the reference's running counter (csc_numba.py:485-493).  Bp[ncols+1] (or An+1), and
+ * Bi / Bx with room for nnz(A) entries; *nnz = entries written.  `rows` must not repeat an index. */
+int csp3_csc_sub_matrix_host(int64_t Am, int64_t An, const int32_t *Ap, const int32_t *Ai, const double *Ax, int64_t nrows,
+                             const int32_t *rows, int64_t ncols, const int32_t *cols, int32_t *Bp, int32_t *Bi, double *Bx,
+                             int64_t *nnz);
+
 /* ---- Newton-Raphson power-flow iteration on the device -------------------- */
 /* The consumer loop the reference's pieces exist for: J = pack_4_by_4(H, N, M, L)
  * (src/CSparse3/csc.py:588-606 -> csc_stack_4_by_4_ff csc_numba.py:640-720), mismatch from Ybus * V

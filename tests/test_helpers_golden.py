@@ -45,8 +45,10 @@ def test_cs_helpers_match_reference(golden_helpers):
     assert nz == int(d["scatter_nz"][0]) and np.array_equal(w, d["scatter_w"]) and np.array_equal(x, d["scatter_x"]) and np.array_equal(Ci, d["scatter_ci"])
 
 
-def test_topology_helpers_match_reference(golden_helpers):
-    """Host forms (numpy glue of the drop-in module); the batched device forms are checked against these in -m gpu."""
+@pytest.mark.gpu
+def test_topology_kernels_match_reference(golden_helpers):
+    """find_islands and the three sub-matrix kernels on the device (topo_kernels.cu) against the reference's outputs,
+    order of the nodes / entries included."""
     d = golden_helpers
     isl = B.find_islands(60, d["Gp"], d["Gi"])
     assert [len(i) for i in isl] == d["islands_len"].tolist()
@@ -81,3 +83,33 @@ def test_csc_add_ff_device_matches_reference(golden_helpers):
     r = B.csc_add_ff(n, n, Ap, Ai, Ax, n, n, Bp, Bi, Bx, -1.25, 3.0)
     nz = int(o[2][-1])
     assert np.array_equal(r[2], o[2]) and np.array_equal(r[3][:nz], o[3][:nz]) and np.array_equal(r[4][:nz], o[4][:nz])
+
+
+@pytest.mark.gpu
+def test_islands_batched_n_minus_1_vs_scipy_and_bridges():
+    """Every branch of the 118-bus and the 10,000-bus synthetic grids removed in turn (one CTA per case): island counts
+    and labels against scipy's connected components; an outage splits the grid exactly when the branch is a bridge."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import connected_components
+    from csparse3_b200 import synth
+    for nb, check_all in ((118, True), (10000, False)):
+        case = synth.GridCase(nb)
+        N, f, t = case.n_bus, case.f, case.t
+        Adj = sp.coo_matrix((np.ones(2 * len(f)), (np.r_[f, t], np.r_[t, f])), shape=(N, N)).tocsc()
+        Adj.sum_duplicates(); Adj.sort_indices()
+        mult = np.asarray(Adj[f, t]).ravel()                      # parallel branches: removing one does not cut the pair
+        of = np.where(mult > 1, -1, f).astype(np.int32); ot = np.where(mult > 1, -1, t).astype(np.int32)
+        label, cnt = B.find_islands_batched(N, Adj.indptr.astype(np.int32), Adj.indices.astype(np.int32), of, ot)
+        bridges = synth._bridges(N, f, t)
+        assert np.array_equal(cnt > 1, bridges)
+        assert (cnt[~bridges] == 1).all() and (label[~bridges] == 0).all()
+        ids = np.arange(len(f)) if check_all else np.r_[np.where(bridges)[0][:40], np.where(~bridges)[0][:10]]
+        for k in ids:
+            A2 = Adj.tolil(copy=True)
+            if of[k] >= 0:
+                A2[f[k], t[k]] = 0; A2[t[k], f[k]] = 0
+            ncomp, lab = connected_components(A2.tocsr(), directed=False)
+            assert ncomp == cnt[k]
+            # same partition; our label is the smallest node of the island
+            first = np.full(ncomp, N); np.minimum.at(first, lab, np.arange(N))
+            assert np.array_equal(label[k], first[lab])

@@ -1,5 +1,6 @@
 """Host-side assembly glue and the CscMat container (no GPU): reference fixtures + scipy."""
 import numpy as np
+import pytest
 import scipy.sparse as sp
 
 from conftest import SIX_BY_THREE
@@ -8,21 +9,28 @@ from csparse3_b200 import csc_b200 as B
 from csparse3_b200 import synth
 
 
-def test_dense_diag_slices_islands():
+@pytest.mark.gpu
+def test_slices_and_islands_run_on_the_device():
+    """CscMat.__getitem__ (reference csc.py:150-292) and CscMat.islands (csc.py:515-521) through topo_kernels.cu."""
+    g = SIX_BY_THREE
+    A = CscMat(g["m"], g["n"], indptr=g["indptr"], indices=g["indices"], data=g["data"])
+    S = sp.csc_matrix((g["data"], g["indices"], g["indptr"]), shape=(6, 3))
+    assert (A[:, 1].todense() == S[:, [1]].toarray()).all()
+    assert (A[:, [0, 2]].todense() == S[:, [0, 2]].toarray()).all()
+    adj = sp.csc_matrix(np.array([[1, 1, 0], [1, 1, 0], [0, 0, 1.0]]))
+    M = scipy_to_mat(adj)
+    assert [i.tolist() for i in M.islands()] == [[0, 1], [2]]
+
+
+def test_dense_diag_norm():
     g = SIX_BY_THREE
     A = CscMat(g["m"], g["n"], indptr=g["indptr"], indices=g["indices"], data=g["data"])
     S = sp.csc_matrix((g["data"], g["indices"], g["indptr"]), shape=(6, 3))
     assert (A.todense() == S.toarray()).all()
-    assert (A[:, 1].todense() == S[:, [1]].toarray()).all()
-    assert (A[:, [0, 2]].todense() == S[:, [0, 2]].toarray()).all()
     assert (Diag(4, 4, 2.5).todense() == 2.5 * np.eye(4)).all()
     assert (Diags(np.array([1.0, 2.0, 3.0])).todense() == np.diag([1.0, 2.0, 3.0])).all()
     assert (A * 5).data.tolist() == (g["data"] * 5).tolist() and A.shape == (6, 3) and A.get_nnz() == 10
     assert A == A.copy() and not (A == (A * 2))
-    # two islands: {0,1} and {2}
-    adj = sp.csc_matrix(np.array([[1, 1, 0], [1, 1, 0], [0, 0, 1.0]]))
-    M = scipy_to_mat(adj)
-    assert [i.tolist() for i in M.islands()] == [[0, 1], [2]]
     assert B.csc_norm(3, g["indptr"], g["data"]) == 28.0
 
 
