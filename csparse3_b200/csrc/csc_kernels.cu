@@ -481,6 +481,82 @@ __device__ void spgemm_column(int j, int tid, int nthr, const i32 *__restrict__ 
     if (BLOCK) __syncthreads(); else __syncwarp();
 }
 
+// ---- short columns: one THREAD per output column --------------------------------------------------------------
+// Power-flow Jacobians and Laplacians multiply into columns with a few dozen candidate products; a warp per column
+// keeps 7 of 32 lanes busy and pays shared-memory atomics.  Here every thread owns a column and keeps its row list
+// SORTED in shared memory ([slot][thread] layout: conflict-free), inserting the products in the reference's loop
+// order (pb outer, pa inner: csc_numba.py:284-293), so every row's sum has the reference's order and no atomics are
+// needed.  The lists of a warp's 32 columns are then written out cooperatively (coalesced).
+constexpr int kThreadProducts = 64;     // columns with at most this many candidate products take the thread path ...
+constexpr int kThreadRows = 32;         // ... in the numeric phase when they have at most this many distinct rows
+constexpr int kThreadCols = 96;         // threads (columns) per CTA (36 KB of static shared memory in the numeric phase)
+
+__device__ __forceinline__ bool spgemm_thread_symbolic(i32 ub) { return ub > 0 && ub <= kThreadProducts; }
+__device__ __forceinline__ bool spgemm_thread_numeric(i32 ub, i32 cnt) { return ub > 0 && ub <= kThreadProducts && cnt <= kThreadRows; }
+
+template <bool NUMERIC>
+__global__ void __launch_bounds__(kThreadCols)
+k_spgemm_thread(int Bn, const i32 *__restrict__ ub, const i32 *__restrict__ Ap, const i32 *__restrict__ Ai,
+                const double *__restrict__ Ax, const i32 *__restrict__ Bp, const i32 *__restrict__ Bi,
+                const double *__restrict__ Bx, i32 *count_out, const i32 *__restrict__ Cp, i32 *Ci, double *Cx)
+{
+    constexpr int SLOTS = NUMERIC ? kThreadRows : kThreadProducts;
+    __shared__ i32 s_key[SLOTS][kThreadCols];
+    __shared__ double s_val[NUMERIC ? SLOTS : 1][NUMERIC ? kThreadCols : 1];
+    __shared__ i32 s_cp[kThreadCols / 32][33];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int j0 = blockIdx.x * kThreadCols; j0 < Bn; j0 += gridDim.x * kThreadCols) {
+        const int j = j0 + t;
+        int len = 0;
+        bool mine = false;
+        if (j < Bn) {
+            const i32 u = __ldg(ub + j);
+            mine = NUMERIC ? spgemm_thread_numeric(u, __ldg(Cp + j + 1) - __ldg(Cp + j)) : spgemm_thread_symbolic(u);
+        }
+        if (mine) {
+            for (int pb = __ldg(Bp + j); pb < __ldg(Bp + j + 1); ++pb) {
+                const int k = __ldg(Bi + pb);
+                const double bv = NUMERIC ? __ldg(Bx + pb) : 0.0;
+                for (int pa = __ldg(Ap + k); pa < __ldg(Ap + k + 1); ++pa) {
+                    const int r = __ldg(Ai + pa);
+                    int i = len;
+                    while (i > 0 && s_key[i - 1][t] > r) --i;
+                    if (i > 0 && s_key[i - 1][t] == r) {
+                        if (NUMERIC) s_val[i - 1][t] = __dadd_rn(s_val[i - 1][t], __dmul_rn(bv, __ldg(Ax + pa)));
+                    } else {
+                        for (int m = len; m > i; --m) { s_key[m][t] = s_key[m - 1][t]; if (NUMERIC) s_val[m][t] = s_val[m - 1][t]; }
+                        s_key[i][t] = r;
+                        if (NUMERIC) s_val[i][t] = __dmul_rn(bv, __ldg(Ax + pa));
+                        ++len;
+                    }
+                }
+            }
+        }
+        if (!NUMERIC) {
+            if (mine) count_out[j] = len;          // (the other kernels add to a zeroed counter; these columns are only ours)
+            continue;
+        }
+        // cooperative write-out: the 32 columns of a warp occupy one contiguous range of Ci / Cx
+        __syncwarp();
+        const int jw = j0 + warp * 32;
+        s_cp[warp][lane] = __ldg(Cp + min(jw + lane, Bn));
+        if (lane == 0) s_cp[warp][32] = __ldg(Cp + min(jw + 32, Bn));
+        __syncwarp();
+        const unsigned have = __ballot_sync(0xffffffffu, mine);
+        const int e0 = s_cp[warp][0], e1 = s_cp[warp][32];
+        for (int e = e0 + lane; e < e1; e += 32) {
+            int lo = 0, hi = 32;                                    // column c with Cp[jw + c] <= e < Cp[jw + c + 1]
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_cp[warp][mid] <= e) lo = mid; else hi = mid; }
+            if ((have >> lo) & 1u) {
+                const int slot = e - s_cp[warp][lo], tt = warp * 32 + lo;
+                Ci[e] = s_key[slot][tt];
+                Cx[e] = s_val[slot][tt];
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // hash-table slots of output column j: 0 = empty column, <= kSmallSlots = a warp with a shared-memory table,
 // more = a CTA with a table in global memory.  ub = candidate products of the column (k_spgemm_ub)
 __device__ __forceinline__ i64 spgemm_slots(i32 ub, i64 Am)
@@ -526,6 +602,7 @@ k_spgemm_small_all(int Bn, i64 Am, const i32 *__restrict__ ub, const i32 *__rest
     for (int j = blockIdx.x * WARPS + warp; j < Bn; j += gridDim.x * WARPS) {
         const i64 slots = spgemm_slots(__ldg(ub + j), Am);
         if (slots <= LO || slots > SLOTS) continue;
+        if (NUMERIC ? spgemm_thread_numeric(__ldg(ub + j), __ldg(Cp + j + 1) - __ldg(Cp + j)) : spgemm_thread_symbolic(__ldg(ub + j))) continue;
         spgemm_column<NUMERIC, false>(j, lane, 32, Ap, Ai, Ax, Bp, Bi, Bx, s_keys[warp],
                                       NUMERIC ? (double *)s_vals[warp] : (double *)nullptr, (unsigned)slots - 1u, count_out, Cp, Ci, Cx,
                                       NUMERIC ? (i32 *)s_compact[warp] : (i32 *)nullptr);
@@ -810,6 +887,9 @@ int spgemm_device(bool numeric, i64 Am, i64 An, const i32 *Ap, const i32 *Ai, co
     {
         constexpr int kTiny = 128, kTinyWarps = 8;
         const int g1 = grid_for(Bn, kTinyWarps, kNumSMs * 8), g2 = grid_for(Bn, kSmallWarps, kNumSMs * 5);
+        const int g0 = grid_for(Bn, kThreadCols, kNumSMs * 16);
+        if (numeric) k_spgemm_thread<true><<<g0, kThreadCols, 0, st>>>((int)Bn, ub.as<i32>(), Ap, Ai, Ax, Bp, Bi, Bx, nullptr, Cp, Ci, Cx);
+        else k_spgemm_thread<false><<<g0, kThreadCols, 0, st>>>((int)Bn, ub.as<i32>(), Ap, Ai, Ax, Bp, Bi, Bx, count, nullptr, nullptr, nullptr);
         if (numeric) {
             k_spgemm_small_all<true, 0, kTiny, kTinyWarps><<<g1, kTinyWarps * 32, 0, st>>>((int)Bn, Am, ub.as<i32>(), Ap, Ai, Ax, Bp, Bi, Bx, nullptr, Cp, Ci, Cx);
             k_spgemm_small_all<true, kTiny, kSmallSlots, kSmallWarps><<<g2, kSmallWarps * 32, 0, st>>>((int)Bn, Am, ub.as<i32>(), Ap, Ai, Ax, Bp, Bi, Bx, nullptr, Cp, Ci, Cx);
