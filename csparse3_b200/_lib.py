@@ -55,6 +55,9 @@ SIGNATURES = {
     "csp3_lu_destroy": [vp],
     "csp3_lu_sizes": [vp, C.POINTER(i64 * 16)],
     "csp3_lu_get_pattern": [vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "csp3_lu_supernodes": [vp, vp, C.POINTER(i64)],
+    "csp3_dmma_peak": [i64, C.POINTER(f64)],
+    "csp3_dense_update_batched": [i64, i64, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp],
     "csp3_lu_get_levels": [vp, cint, vp, vp, vp],
     "csp3_lu_get_program": [vp, cint, vp, i64, vp],
     "csp3_lu_upload": [vp, vp],

@@ -1,4 +1,5 @@
 // api.cu -- extern "C" boundary of libcsparse3_b200.so (declared in include/csparse3_b200.h).
+#include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -528,6 +529,29 @@ int csp3_lu_get_pattern(const csp3_lu_symbolic *sym, int32_t *q, int32_t *pinv, 
     return 0;
 }
 
+int csp3_lu_supernodes(const csp3_lu_symbolic *sym, int32_t *sn_ptr, int64_t *count)
+{
+    if (!sym || !sn_ptr || !count) { set_error("lu_supernodes: bad arguments"); return CSP3_ERR_ARG; }
+    const Factor &F = sym->F;
+    const i64 n = sym->n;
+    // fundamental supernodes of L: column j+1 continues the supernode of j when rows(L(:,j)) \ {j+1} == rows(L(:,j+1))
+    std::vector<i32> a, b;
+    i64 k = 0;
+    sn_ptr[0] = 0;
+    for (i64 j = 0; j + 1 <= n; ++j) {
+        bool cont = false;
+        if (j + 1 < n) {
+            a.assign(F.Li.begin() + F.Lp[(size_t)j] + 1, F.Li.begin() + F.Lp[(size_t)j + 1]);
+            b.assign(F.Li.begin() + F.Lp[(size_t)j + 1] + 1, F.Li.begin() + F.Lp[(size_t)j + 2]);
+            std::sort(a.begin(), a.end()); std::sort(b.begin(), b.end());
+            cont = a.size() == b.size() + 1 && !a.empty() && a[0] == (i32)(j + 1) && std::equal(b.begin(), b.end(), a.begin() + 1);
+        }
+        if (!cont) sn_ptr[++k] = (i32)(j + 1);
+    }
+    *count = k;
+    return 0;
+}
+
 int csp3_lu_get_levels(const csp3_lu_symbolic *sym, int kind, int32_t *level, int32_t *order, int32_t *lptr)
 {
     if (!sym || kind < 0 || kind > 2) { set_error("lu_get_levels: bad arguments"); return CSP3_ERR_ARG; }
@@ -791,9 +815,9 @@ int csp3_lu_refactor_solve_host(csp3_lu_symbolic *sym, int64_t batch, const doub
     const i64 n = D.n, nnzA = D.nnzA;
     if (!G.ready) {
         // The kernels are latency-bound: a chunk costs about the same time whether it holds 500 or 5,000
-        // systems, so chunks are as large as ~512 MB of values allows (kernels of different chunks overlap on
+        // systems, so chunks are as large as ~2 GB of values allows (kernels of different chunks overlap on
         // the device, copies overlap with kernels).
-        i64 chunk = (512ll << 20) / std::max<i64>(nnzA * 8, 1);
+        i64 chunk = (2048ll << 20) / std::max<i64>(nnzA * 8, 1);
         chunk = std::max<i64>(256, std::min<i64>(chunk, 4096));
         chunk = (chunk + 31) & ~31ll;
         G.chunk = chunk;

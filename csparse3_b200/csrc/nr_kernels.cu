@@ -362,9 +362,9 @@ int csp3_nr_solve_host(csp3_nr_plan *plan, int64_t batch, int64_t iters, const d
     auto &G = plan->stage;
     const i64 nb = plan->n_bus, n = plan->n;
     if (!G.ready) {
-        // two chunks in flight on two streams: ~1 GB of Jacobian values each, at most 5,120 cases (the LU kernels are
+        // two chunks in flight on two streams: up to 4 GB of Jacobian values each, at most 5,120 cases (the LU kernels are
         // latency-bound below ~5,000 cases per launch, and two co-resident launches fill the GPU)
-        i64 chunk = (1024ll << 20) / std::max<i64>(plan->jnnz * 8, 1);
+        i64 chunk = (4096ll << 20) / std::max<i64>(plan->jnnz * 8, 1);
         chunk = std::max<i64>(256, std::min<i64>(chunk, 5120));
         chunk = (chunk + 31) & ~31ll;
         G.chunk = chunk;

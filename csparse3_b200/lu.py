@@ -78,6 +78,13 @@ class LuSymbolic:
             return 8 * self.nnz + 8 * self.nnz_lu + 16 * self.n
         return 8 * self.nnz + 16 * self.nnz_lu + 16 * self.n
 
+    def supernodes(self):
+        """First columns of the fundamental supernodes of L -> int32[count + 1] (last entry n)."""
+        sn = np.empty(self.n + 1, dtype=np.int32)
+        cnt = C.c_int64(0)
+        check(_lib.lib().csp3_lu_supernodes(self._h, ptr(sn), C.byref(cnt)), "csp3_lu_supernodes")
+        return sn[:int(cnt.value) + 1].copy()
+
     def levels(self, kind):
         """kind 0 refactor, 1 L-solve, 2 U-solve -> (level[n], order[n], lptr[nlev+1])"""
         nlev = (self.nlev_refactor, self.nlev_lsolve, self.nlev_usolve)[kind]

@@ -175,6 +175,10 @@ int csp3_lu_get_pattern(const csp3_lu_symbolic *sym, int32_t *q, int32_t *pinv, 
                         int32_t *Up, int32_t *Ui, double *Lx, double *Ux);
 /* Level sets.  kind 0 refactor (from U), 1 L-solve, 2 U-solve.  level[n], order[n], lptr[nlev+1]. */
 int csp3_lu_get_levels(const csp3_lu_symbolic *sym, int kind, int32_t *level, int32_t *order, int32_t *lptr);
+/* Fundamental supernodes of L (maximal runs of columns j, j+1, ... whose patterns nest: rows(L(:,j)) minus {j+1} equals
+ * rows(L(:,j+1))): sn_ptr[0..count] are the first columns of the supernodes, sn_ptr[count] = n (room for n + 1 entries).
+ * The dense trailing update of a wide supernode is what csp3_dense_update_batched computes on the FP64 tensor cores. */
+int csp3_lu_supernodes(const csp3_lu_symbolic *sym, int32_t *sn_ptr, int64_t *count);
 /* Introspection of the compiled device programs (csparse3_b200/csrc/program.hpp): which = 0 refactor, 1 forward
  * sweep, 2 backward sweep (row-oriented), 3 wide refactor, 4 / 5 wide forward / backward sweep.  Returns the size in bytes (copied into buf when
  * capacity allows), or a negative error.  geometry (optional, 8 values): [0] stage bytes; wide refactor only:
@@ -234,6 +238,16 @@ int csp3_lu_solve_host(csp3_lu_symbolic *sym, int64_t batch, const double *Lx, c
  * b is overwritten with x.  Host pointers. */
 int csp3_csc_lusol_host(int64_t order, int64_t n, const int32_t *Ap, const int32_t *Ai, const double *Ax,
                         double *b, double tol);
+
+/* ---- FP64 tensor-core building blocks (groundwork for supernodal trailing updates, BASELINE.json configs[4]) -------- */
+/* Measured DMMA (mma.sync.m8n8k4.f64) throughput of the current device in TFLOP/s: `iters` instructions per warp per
+ * accumulator chain, best of 5 launches, CUDA events. */
+int csp3_dmma_peak(int64_t iters, double *tflops);
+/* C_s -= A_s * B_s for s < batch: column-major blocks A[m x k] (lda), B[k x n] (ldb), C[m x n] (ldc), system s at
+ * offset s * stride (doubles).  This is the trailing update L21 * U12 of one supernode for every system of a
+ * same-pattern batch; a warp owns a 32 x 32 tile of C and issues DMMA.8x8x4.  DEVICE pointers, stream-ordered. */
+int csp3_dense_update_batched(int64_t batch, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda, int64_t strideA,
+                              const double *B, int64_t ldb, int64_t strideB, double *C, int64_t ldc, int64_t strideC, void *stream);
 
 /* ---- topology operations on the device ------------------------------------------- */
 /* Replaces find_islands(node_number, indptr, indices), src/CSparse3/csc_numba.py:743-808 (caller CscMat.islands,

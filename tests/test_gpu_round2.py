@@ -169,3 +169,28 @@ def test_transpose_with_dense_rows_and_spgemm_with_big_columns():
     assert nnz == onnz and np.array_equal(Cp, Op)
     order = np.lexsort((Oi, np.repeat(np.arange(k), np.diff(Op))))
     assert np.array_equal(Ci, Oi[order]) and np.array_equal(Cx, Ox[order])
+
+
+def test_dmma_dense_update_and_supernodes():
+    """Groundwork for config 5's supernodal trailing updates: the batched DMMA update C -= A B against numpy, the
+    measured FP64 tensor throughput, and the supernode structure of Laplacian factors (wide supernodes exist only
+    near the top of the elimination tree)."""
+    import torch
+    from csparse3_b200 import dense
+    rng = np.random.default_rng(2)
+    for (batch, m, n, k) in ((3, 70, 45, 19), (2, 256, 128, 64), (1, 8, 8, 4)):
+        A = rng.standard_normal((batch, k, m)); Bm = rng.standard_normal((batch, n, k)); Cm = rng.standard_normal((batch, n, m))
+        ref = Cm - np.einsum("skm,snk->snm", A, Bm)            # column-major blocks: (A^T B^T)^T per system
+        out = dense.dense_update(torch.as_tensor(A).cuda(), torch.as_tensor(Bm).cuda(), torch.as_tensor(Cm).cuda()).cpu().numpy()
+        assert np.abs(out - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), (batch, m, n, k)
+    tf = dense.dmma_peak(2048)
+    assert 5.0 < tf < 200.0, tf
+    n_, Ap, Ai, Ax = synth.laplacian_3d(12)
+    sym = LuSymbolic(n_, Ap, Ai, Ax, order=1, tol=1.0)
+    sn = sym.supernodes()
+    w = np.diff(sn)
+    assert sn[0] == 0 and sn[-1] == n_ and (w >= 1).all() and w.max() >= 16
+    # nesting: inside a supernode every column's pattern is the previous one's minus its own row
+    j = int(sn[np.argmax(w)])
+    r0 = set(sym.Li[sym.Lp[j] + 1:sym.Lp[j + 1]]); r1 = set(sym.Li[sym.Lp[j + 1] + 1:sym.Lp[j + 2]])
+    assert r0 - {j + 1} == r1
