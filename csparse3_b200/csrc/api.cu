@@ -37,6 +37,7 @@ Tuning &tuning()
         v.wide_S = env("CSP3_WIDE_S"); v.wide_R = env("CSP3_WIDE_LANE"); v.wide_ring = env("CSP3_WIDE_R"); v.wide_stage = env("CSP3_WIDE_F");
         v.wide_budget = env("CSP3_WIDE_BUDGET");
         if (getenv("CSP3_PANEL")) v.panel = env("CSP3_PANEL");
+        if (getenv("CSP3_TMEM")) v.tmem = env("CSP3_TMEM");
         v.panel_fma = env("CSP3_PANEL_FMA");
         v.panel_budget = env("CSP3_PANEL_BUDGET");
         return v;

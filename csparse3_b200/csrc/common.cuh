@@ -67,6 +67,8 @@ bool use_wide(const DevSchedule &D, i64 batch);
 int launch_refactor_wide(const DevSchedule &D, i64 batch, const double *Ax, double *Lw, double *Uw, i32 *status,
                          cudaStream_t st);
 bool use_panel(const DevSchedule &D, i64 batch);
+bool use_tmem(const DevSchedule &D, i64 batch);
+int launch_refactor_tmem(const DevSchedule &D, i64 batch, const double *Ax, double *Lw, double *Uw, i32 *status, cudaStream_t st);
 int launch_growth(const DevSchedule &D, i64 batch, const double *Lw, double *growth, cudaStream_t st);
 int launch_refactor_panel(const DevSchedule &D, i64 batch, const double *Ax, double *Lw, double *Uw, i32 *status,
                           double *growth, cudaStream_t st);
@@ -78,6 +80,7 @@ int launch_solve_wide(const DevSchedule &D, i64 batch, const double *Lw, const d
 // 0 = automatic)
 struct Tuning {
     int rf_S = 0, sv_S = 0, ws_S = 0, rf_win = 0, sv_stage = 0;
+    int tmem = 0;                          // CSP3_TMEM=1: experimental refactor kernel with the accumulator in tensor memory (lu_refactor_tmem_kernel)
     int panel = 0, panel_fma = 0, panel_budget = 0;          // CSP3_PANEL=1 selects the experimental panel refactor kernel (lu_panel.cu), CSP3_PANEL_FMA (fused multiply-add, not bit-exact)
     int wide = 1, wide_solve = 1, wide_S = 0, wide_R = 0, wide_ring = 0, wide_stage = 0, wide_budget = 0;   // CSP3_WIDE (0 disables), CSP3_WIDE_S/_R/_F/_BUDGET
 };

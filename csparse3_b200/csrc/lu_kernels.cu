@@ -434,6 +434,7 @@ bool use_panel(const DevSchedule &D, i64 batch)
     (void)batch;
     return D.panel_ok && tuning().panel != 0 && tuning().ws_S == 0 && (!D.wide_ok || D.wide_S == 8);
 }
+// (use_tmem: lu_wide.cu.  With the panel kernel selected the factors stay in 8-system bundles.)
 
 int workspace_bundle_width(const DevSchedule &D, i64 batch)
 {
@@ -472,7 +473,7 @@ __global__ void lu_growth_kernel(i64 batch, int lnz, int S, const uint8_t *__res
 int launch_growth(const DevSchedule &D, i64 batch, const double *Lw, double *growth, cudaStream_t st)
 {
     if (batch <= 0) return 0;
-    const int S = workspace_bundle_width(D, batch);
+    const int S = use_tmem(D, batch) ? 32 : workspace_bundle_width(D, batch);
     lu_growth_kernel<<<(unsigned)((batch + S - 1) / S), 256, 0, st>>>(batch, D.lnz, S, D.d_ldiag, Lw, growth);
     CSP3_CUDA(cudaGetLastError());
     return 0;
@@ -483,6 +484,7 @@ int launch_refactor(const DevSchedule &D, i64 batch, const double *Ax, double *L
 {
     if (batch <= 0) return 0;
     if (interleaved && use_panel(D, batch)) return launch_refactor_panel(D, batch, Ax, Lx, Ux, status, nullptr, st);
+    if (interleaved && use_tmem(D, batch)) return launch_refactor_tmem(D, batch, Ax, Lx, Ux, status, st);
     if (interleaved && use_wide(D, batch)) return launch_refactor_wide(D, batch, Ax, Lx, Ux, status, st);
     RefactorArgs a;
     a.prog = D.rf_prog; a.prog_bytes = D.rf_prog_bytes; a.prog_stage = D.rf_prog_stage;

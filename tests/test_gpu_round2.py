@@ -118,14 +118,17 @@ def test_pivot_growth_is_detected_and_repivoted():
         assert np.linalg.norm(Ak @ xh[k] - b[k]) <= 1e-10 * np.linalg.norm(b[k]), k
 
 
-@pytest.mark.parametrize("env", [{"CSP3_PANEL": "1"}, {"CSP3_PANEL": "1", "CSP3_PANEL_FMA": "1"}])
-def test_panel_refactor_kernel_parity(env):
-    """The experimental panel kernel (lu_panel.cu): bit-exact in exact mode, within 1e-9 with fused multiply-add.
-    The knob is read once per process, so the check runs in a child process."""
+@pytest.mark.parametrize("env", [{"CSP3_PANEL": "1"}, {"CSP3_PANEL": "1", "CSP3_PANEL_FMA": "1"}, {"CSP3_TMEM": "1"}])
+def test_panel_and_tmem_refactor_kernel_parity(env):
+    """The experimental refactor kernels: the panel kernel (lu_panel.cu; bit-exact in exact mode, within 1e-9 with fused
+    multiply-add) and the kernel that keeps the accumulator in tensor memory (lu_refactor_tmem_kernel: same program as
+    the wide kernel, tcgen05.ld / .st as a per-lane scratchpad, factors in 32-system bundles; used for the 2,000-bus
+    pattern, the 118-bus one exceeds its shared-memory budget and takes the wide kernel).  The knobs are read once
+    per process, so the check runs in a child process."""
     code = (
         "import sys; sys.path.insert(0, %r); import numpy as np, torch\n"
         "from csparse3_b200 import synth; from csparse3_b200.lu import LuSymbolic; from oracle import oracle as orc\n"
-        "for nb, B in ((118, 37), (2000, 19)):\n"
+        "for nb, B in ((118, 37), (2000, 71)):\n"
         "    g = synth.GridCase(nb); n, Ap, Ai, Ax0 = g.base_jacobian(); sym = LuSymbolic(n, Ap, Ai, Ax0)\n"
         "    Ax, b = g.jacobian_batch(0, B)\n"
         "    work = sym.workspace(B, 'cuda'); st = sym.refactor_ws(torch.as_tensor(Ax).cuda(), work)\n"
