@@ -495,9 +495,8 @@ def main():
         Bmax = -(-total // world)                                   # the largest shard bounds the step
         bytes_rf = (8 * sym.nnz + 8 * sym.nnz_lu) * Bmax           # read A, write L+U
         bytes_sv = (8 * sym.nnz_lu + 16 * n) * Bmax                # read L+U, read b, write x
-        panel = os.environ.get("CSP3_PANEL", "0") not in ("", "0")
         wide = sym.wide_width > 0 and os.environ.get("CSP3_WIDE", "1") != "0"
-        rf_name = "lu_refactor_panel_kernel" if panel else ("lu_refactor_wide_kernel" if wide else "lu_refactor_kernel")
+        rf_name = sym.refactor_kernel_name(Bmax)
         sv_name = "lu_sweep_wide_kernel" if wide else "lu_solve_kernel"
         dom = (rf_name, bytes_rf, rf_ms) if rf_ms >= sv_ms else (sv_name, bytes_sv, sv_ms)
         achieved = dom[1] / (dom[2] * 1e-3) / 1e9

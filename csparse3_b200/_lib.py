@@ -64,6 +64,7 @@ SIGNATURES = {
     "csp3_lu_refactor_batched": [vp, i64, vp, vp, vp, vp, vp],
     "csp3_lu_solve_batched": [vp, i64, vp, vp, vp, vp, vp],
     "csp3_lu_workspace_bytes": [vp, i64],
+    "csp3_lu_refactor_kernel_name": [vp, i64],
     "csp3_lu_refactor_solve_batched": [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp],
     "csp3_lu_refactor_ws": [vp, i64, vp, vp, vp, vp],
     "csp3_lu_solve_ws": [vp, i64, vp, vp, vp, vp],
@@ -83,7 +84,7 @@ SIGNATURES = {
     "csp3_nr_solve": [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp],
     "csp3_nr_solve_host": [vp, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp],
 }
-_RESTYPE = {"csp3_last_error_string": C.c_char_p, "csp3_lu_workspace_bytes": i64, "csp3_lu_get_program": i64,
+_RESTYPE = {"csp3_last_error_string": C.c_char_p, "csp3_lu_refactor_kernel_name": C.c_char_p, "csp3_lu_workspace_bytes": i64, "csp3_lu_get_program": i64,
              "csp3_nr_workspace_bytes": i64}
 
 _lib = None

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "csc_kernels.cuh"
 #include "panel_program.hpp"
+#include "rowlane_program.hpp"
 
 namespace csp3 {
 
@@ -38,6 +39,8 @@ Tuning &tuning()
         v.wide_budget = env("CSP3_WIDE_BUDGET");
         if (getenv("CSP3_PANEL")) v.panel = env("CSP3_PANEL");
         if (getenv("CSP3_TMEM")) v.tmem = env("CSP3_TMEM");
+        if (getenv("CSP3_ROWLANE")) v.rowlane = env("CSP3_ROWLANE");
+        v.rl_warps = env("CSP3_RL_WARPS");
         v.panel_fma = env("CSP3_PANEL_FMA");
         v.panel_budget = env("CSP3_PANEL_BUDGET");
         return v;
@@ -100,6 +103,7 @@ struct csp3_lu_symbolic {
     WideProgram W;                     // wide refactor program (ok == false: pattern does not fit, v3 kernels are used)
     WideSweep WF, WB;                  // wide forward / backward sweep programs
     PanelProgram PP;                   // panel refactor program (lu_panel.cu); ok == false: the wide / v3 kernels are used
+    RowlaneProgram RL;                 // row-lane refactor program (lu_rowlane.cu)
     std::vector<i32> qinv;             // x[c] = x_pivot_order[qinv[c]]
     DevSchedule dev[kMaxDevices];
     // staging for csp3_lu_refactor_solve_host (per device, lazily created)
@@ -134,6 +138,16 @@ static void compile_wide(csp3_lu_symbolic &Sy)
             if (t.panel_budget > 0) break;
         }
         if (!ok) Sy.PP = PanelProgram();
+    }
+    if (Sy.n > 0) {
+        const char *why = "";
+        if (!compile_rowlane_refactor(Sy.n, Sy.Ap.data(), Sy.q, Sy.F, Sy.S, Sy.RL, &why)) {
+            if (getenv("CSP3_DEBUG")) fprintf(stderr, "csp3: row-lane refactor unavailable: %s\n", why);
+            Sy.RL = RowlaneProgram();
+        } else if (getenv("CSP3_DEBUG")) {
+            fprintf(stderr, "csp3: row-lane program: %d quads (%lld update quads with %lld records, %lld late), %lld ops, %d slots, %lld conflict pairs\n", Sy.RL.quads,
+                    (long long)Sy.RL.update_quads, (long long)Sy.RL.update_records, (long long)Sy.RL.late_quads, (long long)Sy.RL.ops, Sy.RL.nslots, (long long)Sy.RL.conflict_pairs);
+        }
     }
     if (t.wide == 0 || Sy.n == 0) return;
     const i32 width = (t.wide_S == 4 || t.wide_S == 16 || t.wide_S == 32) ? t.wide_S : 8;
@@ -577,6 +591,17 @@ int64_t csp3_lu_get_program(const csp3_lu_symbolic *sym, int which, uint8_t *buf
         case 6: P = sym->PP.ok ? &sym->PP.prog : nullptr; break;
         default: break;
     }
+    if (which == 7) {                                    // row-lane program: 44 words per quad (rowlane_program.hpp)
+        if (!sym->RL.ok) { set_error("lu_get_program: program %d not available", which); return CSP3_ERR_ARG; }
+        const std::vector<uint32_t> &v = sym->RL.words;
+        if (geometry) {
+            std::memset(geometry, 0, 8 * sizeof(int64_t));
+            geometry[0] = sym->RL.update_quads; geometry[1] = kRlStageQuads; geometry[2] = sym->RL.nslots; geometry[3] = sym->RL.late_quads;
+            geometry[4] = sym->RL.ops; geometry[5] = sym->RL.quads; geometry[6] = (i64)sym->RL.smem_bytes; geometry[7] = sym->RL.update_records;
+        }
+        if (buf && capacity >= (int64_t)(v.size() * 4)) std::memcpy(buf, v.data(), v.size() * 4);
+        return (int64_t)(v.size() * 4);
+    }
     if (!P) { set_error("lu_get_program: program %d not available", which); return CSP3_ERR_ARG; }
     if (geometry) {
         std::memset(geometry, 0, 8 * sizeof(int64_t));
@@ -652,6 +677,7 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
     const size_t i_wfs = add(sym->WF.prog.bytes.data(), wsolve ? sym->WF.prog.bytes.size() : 0);
     const size_t i_wbs = add(sym->WB.prog.bytes.data(), wsolve ? sym->WB.prog.bytes.size() : 0);
     const size_t i_prf = add(sym->PP.prog.bytes.data(), sym->PP.ok ? sym->PP.prog.bytes.size() : 0);
+    const size_t i_rl = add(sym->RL.words.data(), sym->RL.ok ? sym->RL.words.size() * 4 : 0);
     std::vector<uint8_t> ldiag(F.Li.size(), 0);
     for (i64 k = 0; k < sym->n; ++k) ldiag[(size_t)F.Lp[(size_t)k]] = 1;
     const size_t i_ldiag = add(ldiag.data(), ldiag.size());
@@ -700,6 +726,11 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
         D.prf_prog = (const uint8_t *)at(i_prf); D.prf_prog_bytes = (i32)sym->PP.prog.bytes.size();
         D.prf_nslots = sym->PP.nslots; D.prf_lsrc = sym->PP.ring + sym->PP.landing; D.prf_steps = sym->PP.steps; D.prf_smem = sym->PP.smem_bytes;
     }
+    if (sym->RL.ok && sym->RL.smem_bytes <= (size_t)200 * 1024) {
+        D.rl_ok = true;
+        D.rl_prog = (const uint8_t *)at(i_rl);
+        D.rl_quads = sym->RL.quads; D.rl_nslots = sym->RL.nslots;
+    }
     D.d_ldiag = (const uint8_t *)at(i_ldiag);
     D.ready = true;
     return 0;
@@ -715,6 +746,17 @@ static const DevSchedule *current_schedule(const csp3_lu_symbolic *sym)
         return nullptr;
     }
     return &sym->dev[devid];
+}
+
+const char *csp3_lu_refactor_kernel_name(const csp3_lu_symbolic *sym, int64_t batch)
+{
+    const DevSchedule *D = current_schedule(sym);
+    if (!D) return nullptr;
+    if (use_panel(*D, batch)) return "lu_refactor_panel_kernel";
+    if (use_rowlane(*D, batch)) return "lu_refactor_rowlane_kernel";
+    if (use_tmem(*D, batch)) return "lu_refactor_tmem_kernel";
+    if (use_wide(*D, batch)) return "lu_refactor_wide_kernel";
+    return "lu_refactor_kernel";
 }
 
 int csp3_lu_refactor_batched(const csp3_lu_symbolic *sym, int64_t batch, const double *Ax, double *Lx,

@@ -434,11 +434,21 @@ bool use_panel(const DevSchedule &D, i64 batch)
     (void)batch;
     return D.panel_ok && tuning().panel != 0 && tuning().ws_S == 0 && (!D.wide_ok || D.wide_S == 8);
 }
+bool use_rowlane(const DevSchedule &D, i64 batch)
+{
+    (void)batch;
+    if (!D.rl_ok || tuning().rowlane == 0 || tuning().ws_S != 0 || !D.wide_ok || D.wide_S != 8 || !D.wide_solve_ok) return false;
+    if (tuning().rowlane > 0) return true;                       // CSP3_ROWLANE=1: always
+    // automatic: the wide refactor keeps accumulator, L cache and landing area of a bundle in shared memory and is the
+    // faster kernel while >= 5 bundles per SM are resident (config 3: 24.8 KB, 6.6 ms against 9.7 ms); patterns with
+    // long columns leave 3 bundles per SM (config 4: 57 KB, 80.9 ms) where the row-lane kernel (9 KB) needs 60.9 ms
+    return D.wrf_smem > (size_t)40 * 1024;
+}
 // (use_tmem: lu_wide.cu.  With the panel kernel selected the factors stay in 8-system bundles.)
 
 int workspace_bundle_width(const DevSchedule &D, i64 batch)
 {
-    if (use_panel(D, batch)) return 8;
+    if (use_panel(D, batch) || use_rowlane(D, batch)) return 8;
     if (use_wide(D, batch)) return D.wide_S;
     const int S = tuning().ws_S;
     if (S == 2 || S == 4 || S == 8 || S == 16) return S;
@@ -484,6 +494,7 @@ int launch_refactor(const DevSchedule &D, i64 batch, const double *Ax, double *L
 {
     if (batch <= 0) return 0;
     if (interleaved && use_panel(D, batch)) return launch_refactor_panel(D, batch, Ax, Lx, Ux, status, nullptr, st);
+    if (interleaved && use_rowlane(D, batch)) return launch_refactor_rowlane(D, batch, Ax, Lx, Ux, status, st);
     if (interleaved && use_tmem(D, batch)) return launch_refactor_tmem(D, batch, Ax, Lx, Ux, status, st);
     if (interleaved && use_wide(D, batch)) return launch_refactor_wide(D, batch, Ax, Lx, Ux, status, st);
     RefactorArgs a;

@@ -186,6 +186,16 @@ class LuSymbolic:
                 status.data_ptr(), None if work is None else work.data_ptr(), st), "csp3_lu_refactor_solve_batched")
         return x, status
 
+    def refactor_kernel_name(self, batch, device=None):
+        """Kernel the workspace path runs for `batch` systems on the current (or given) device."""
+        import torch
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._upload(dev.index if dev.index is not None else torch.cuda.current_device(), None)
+        name = _lib.lib().csp3_lu_refactor_kernel_name(self._h, int(batch))
+        if name is None:
+            raise RuntimeError(_lib.last_error())
+        return name.decode()
+
     def refactor_ws(self, Ax, work, status=None):
         """Refactor into the internal bundle-interleaved factor workspace (fast path, see workspace())."""
         import torch

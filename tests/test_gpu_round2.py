@@ -118,7 +118,8 @@ def test_pivot_growth_is_detected_and_repivoted():
         assert np.linalg.norm(Ak @ xh[k] - b[k]) <= 1e-10 * np.linalg.norm(b[k]), k
 
 
-@pytest.mark.parametrize("env", [{"CSP3_PANEL": "1"}, {"CSP3_PANEL": "1", "CSP3_PANEL_FMA": "1"}, {"CSP3_TMEM": "1"}])
+@pytest.mark.parametrize("env", [{"CSP3_PANEL": "1"}, {"CSP3_PANEL": "1", "CSP3_PANEL_FMA": "1"}, {"CSP3_TMEM": "1"},
+                                 {"CSP3_ROWLANE": "1"}, {"CSP3_ROWLANE": "1", "CSP3_RL_WINDOW": "1"}])
 def test_panel_and_tmem_refactor_kernel_parity(env):
     """The experimental refactor kernels: the panel kernel (lu_panel.cu; bit-exact in exact mode, within 1e-9 with fused
     multiply-add) and the kernel that keeps the accumulator in tensor memory (lu_refactor_tmem_kernel: same program as

@@ -1,0 +1,86 @@
+"""CPU validation of the compiled "row-lane" refactor program (csparse3_b200/csrc/rowlane_program.cpp): the
+interpreter of tests/rowlane_interp.py (which models the kernel's operand look-ahead) must reproduce the oracle's
+factors bit for bit, with every multiply-subtract executed once."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from csparse3_b200 import synth
+from csparse3_b200.lu import LuSymbolic
+from oracle import oracle as orc
+
+import rowlane_interp as ri
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _check(n, Ap, Ai, Axb, order=1, tol=1e-3):
+    sym = LuSymbolic(n, Ap, Ai, Axb[0], order=order, tol=tol)
+    Lx, Ux, fail, stats = ri.run_refactor(sym, Axb)
+    oL, oU = [], []
+    for k in range(Axb.shape[0]):
+        L, U = orc.csc_lu_refactor(n, Ap, Ai, Axb[k], sym.q, sym.pinv, sym.Lp, sym.Li, sym.Up, sym.Ui)
+        oL.append(L); oU.append(U)
+    assert (fail == 0).all()
+    assert np.array_equal(Ux, np.array(oU)) and np.array_equal(Lx, np.array(oL))
+    assert stats["ops"] * 2 == sym.flops                       # every update operation exactly once
+    return sym, stats
+
+
+def test_rowlane_program_grid118():
+    g = synth.GridCase(118)
+    n, Ap, Ai, Ax0 = g.base_jacobian()
+    Axb, _ = g.jacobian_batch(0, 4)
+    _check(n, Ap, Ai, Axb)
+
+
+def test_rowlane_program_config3_pattern():
+    g = synth.GridCase(2000)
+    n, Ap, Ai, Ax0 = g.base_jacobian()
+    Axb, _ = g.jacobian_batch(0, 2)
+    sym, stats = _check(n, Ap, Ai, Axb)
+    # the column order keeps late operand reads rare and the accumulator is a few KB per bundle
+    assert stats["late_quads"] <= 0.05 * stats["update_quads"]
+    assert ri.get_program(sym)[1][6] <= 11 * 1024
+
+
+@pytest.mark.parametrize("order,tol", [(1, 1e-3), (2, 1.0), (0, 1.0), (3, 0.1)])
+def test_rowlane_program_small_matrices(order, tol):
+    rng = np.random.default_rng(order)
+    cases = [synth.laplacian_2d(9), synth.laplacian_3d(5), (1, np.array([0, 1], dtype=np.int32), np.array([0], dtype=np.int32), np.array([2.0]))]
+    for t in range(5):
+        n = int(rng.integers(2, 150))
+        A = sp.csc_matrix(sp.random(n, n, density=min(1.0, 3.0 / n + 0.03), random_state=int(rng.integers(1 << 30)),
+                                    format="csc") + sp.diags(rng.uniform(0.5, 2.0, n)))
+        cases.append((n, A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()))
+    for n, Ap, Ai, Ax in cases:
+        Axb = Ax[None, :] * rng.uniform(0.9, 1.1, (3, len(Ax)))
+        Axb[0] = Ax
+        _check(n, Ap, Ai, Axb, order=order, tol=tol)
+
+
+def test_rowlane_program_reports_bad_pivots():
+    Ap = np.array([0, 1, 2, 5], dtype=np.int32); Ai = np.array([0, 1, 0, 1, 2], dtype=np.int32)
+    Ax = np.array([2.0, 3.0, 1.0, 1.0, 4.0])
+    sym = LuSymbolic(3, Ap, Ai, Ax, order=0, tol=1.0)
+    Axb = np.tile(Ax, (3, 1))
+    Axb[1, 4] = 0.0
+    Axb[2, 4] = np.inf
+    _, _, fail, _ = ri.run_refactor(sym, Axb)
+    assert fail.tolist() == [0, 3, 3]
+
+
+@pytest.mark.parametrize("env", [
+{"CSP3_RL_WINDOW": "1"}, {"CSP3_RL_WINDOW": "4"}])
+def test_rowlane_program_other_geometries(env):
+    """Other look-ahead depths / the natural column order (every chain reads late): knobs are read per process."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import numpy as np; "
+            "import test_rowlane_program as t; from csparse3_b200 import synth; g = synth.GridCase(118); "
+            "n, Ap, Ai, Ax0 = g.base_jacobian(); Axb, bb = g.jacobian_batch(0, 3); t._check(n, Ap, Ai, Axb); print('ok')"
+            ) % (ROOT, os.path.join(ROOT, "tests"))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
