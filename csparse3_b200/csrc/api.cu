@@ -40,7 +40,7 @@ Tuning &tuning()
         if (getenv("CSP3_PANEL")) v.panel = env("CSP3_PANEL");
         if (getenv("CSP3_TMEM")) v.tmem = env("CSP3_TMEM");
         if (getenv("CSP3_ROWLANE")) v.rowlane = env("CSP3_ROWLANE");
-        v.rl_warps = env("CSP3_RL_WARPS");
+        v.rl_warps = env("CSP3_RL_W"); v.rl_nq = env("CSP3_RL_NQ");
         v.panel_fma = env("CSP3_PANEL_FMA");
         v.panel_budget = env("CSP3_PANEL_BUDGET");
         return v;
@@ -103,7 +103,9 @@ struct csp3_lu_symbolic {
     WideProgram W;                     // wide refactor program (ok == false: pattern does not fit, v3 kernels are used)
     WideSweep WF, WB;                  // wide forward / backward sweep programs
     PanelProgram PP;                   // panel refactor program (lu_panel.cu); ok == false: the wide / v3 kernels are used
-    RowlaneProgram RL;                 // row-lane refactor program (lu_rowlane.cu)
+    RowlaneProgram RL[kRlVariants];    // row-lane refactor programs (lu_rowlane.cu), one per geometry, compiled on first use
+    bool RLtried[kRlVariants] = {};
+    std::mutex rl_mu;                  // guards RL / RLtried and the per-device variants (taken inside calls that may hold `mu`)
     std::vector<i32> qinv;             // x[c] = x_pivot_order[qinv[c]]
     DevSchedule dev[kMaxDevices];
     // staging for csp3_lu_refactor_solve_host (per device, lazily created)
@@ -139,16 +141,6 @@ static void compile_wide(csp3_lu_symbolic &Sy)
         }
         if (!ok) Sy.PP = PanelProgram();
     }
-    if (Sy.n > 0) {
-        const char *why = "";
-        if (!compile_rowlane_refactor(Sy.n, Sy.Ap.data(), Sy.q, Sy.F, Sy.S, Sy.RL, &why)) {
-            if (getenv("CSP3_DEBUG")) fprintf(stderr, "csp3: row-lane refactor unavailable: %s\n", why);
-            Sy.RL = RowlaneProgram();
-        } else if (getenv("CSP3_DEBUG")) {
-            fprintf(stderr, "csp3: row-lane program: %d quads (%lld update quads with %lld records, %lld late), %lld ops, %d slots, %lld conflict pairs\n", Sy.RL.quads,
-                    (long long)Sy.RL.update_quads, (long long)Sy.RL.update_records, (long long)Sy.RL.late_quads, (long long)Sy.RL.ops, Sy.RL.nslots, (long long)Sy.RL.conflict_pairs);
-        }
-    }
     if (t.wide == 0 || Sy.n == 0) return;
     const i32 width = (t.wide_S == 4 || t.wide_S == 16 || t.wide_S == 32) ? t.wide_S : 8;
     const int ctas_per_sm[4] = {(10000 / width + kNumSMs - 1) / kNumSMs, 0, 0, 0};
@@ -174,6 +166,59 @@ static void compile_wide(csp3_lu_symbolic &Sy)
     }
     Sy.W = WideProgram();
 }
+
+// row-lane program of one geometry: compiled on first use (host), cached in the symbolic object
+static RowlaneProgram *rowlane_program(csp3_lu_symbolic &Sy, int variant)
+{
+    if (variant < 0 || variant >= kRlVariants || Sy.n <= 0) return nullptr;
+    if (!Sy.RLtried[variant]) {
+        Sy.RLtried[variant] = true;
+        const Tuning &t = tuning();
+        i32 rw = kRlGeometry[variant][0], rq = kRlGeometry[variant][1];
+        if (variant == kRlVariants - 1) {
+            rw = (t.rl_warps == 2 || t.rl_warps == 4 || t.rl_warps == 8) ? t.rl_warps : 1;
+            rq = (t.rl_nq >= 1 && t.rl_nq <= 3) ? t.rl_nq : 3;
+        }
+        const char *why = "";
+        RowlaneProgram &P = Sy.RL[variant];
+        if (!compile_rowlane_refactor(Sy.n, Sy.Ap.data(), Sy.q, Sy.F, Sy.S, rw, rq, P, &why)) {
+            if (getenv("CSP3_DEBUG")) fprintf(stderr, "csp3: row-lane refactor unavailable: %s\n", why);
+            P = RowlaneProgram();
+        } else if (getenv("CSP3_DEBUG")) {
+            fprintf(stderr, "csp3: row-lane program: %d warps x %d quads per stage, %d quads (longest stream %d; %lld update quads with %lld records, %lld late, %lld records read another warp's column, %lld empty quads), %lld ops, %d slots, %lld conflict pairs\n",
+                    P.warps, P.stage_quads, P.quads, *std::max_element(P.stream_quads, P.stream_quads + kRlMaxWarps), (long long)P.update_quads,
+                    (long long)P.update_records, (long long)P.late_quads, (long long)P.cross_records, (long long)P.pad_quads, (long long)P.ops, P.nslots, (long long)P.conflict_pairs);
+        }
+    }
+    return Sy.RL[variant].ok ? &Sy.RL[variant] : nullptr;
+}
+
+namespace csp3 {
+int ensure_rowlane_variant(const DevSchedule &D, int variant)
+{
+    if (variant < 0 || variant >= kRlVariants || !D.owner) return -1;
+    DevSchedule::RlVariant &R = D.rl[variant];
+    if (R.tried) return R.ok ? 0 : -1;
+    csp3_lu_symbolic &Sy = *static_cast<csp3_lu_symbolic *>(D.owner);
+    std::lock_guard<std::mutex> lock(Sy.rl_mu);
+    if (R.tried) return R.ok ? 0 : -1;
+    const RowlaneProgram *P = rowlane_program(Sy, variant);
+    if (P && P->smem_bytes <= (size_t)200 * 1024) {
+        uint8_t *dev = nullptr;
+        const size_t bytes = P->words.size() * 4;
+        if (cudaMalloc((void **)&dev, bytes) == cudaSuccess && cudaMemcpy(dev, P->words.data(), bytes, cudaMemcpyHostToDevice) == cudaSuccess) {
+            R.prog = dev; R.quads = P->quads; R.nslots = P->nslots; R.warps = P->warps; R.stage_quads = P->stage_quads; R.smem = P->smem_bytes;
+            for (int w = 0; w < kRlMaxWarps; ++w) R.stream_off[w] = (i32)P->stream_off[w];
+            R.ok = true;
+        } else {
+            if (dev) cudaFree(dev);
+            cudaGetLastError();
+        }
+    }
+    R.tried = true;
+    return R.ok ? 0 : -1;
+}
+}  // namespace csp3
 
 extern "C" {
 
@@ -592,12 +637,17 @@ int64_t csp3_lu_get_program(const csp3_lu_symbolic *sym, int which, uint8_t *buf
         default: break;
     }
     if (which == 7) {                                    // row-lane program: 44 words per quad (rowlane_program.hpp)
-        if (!sym->RL.ok) { set_error("lu_get_program: program %d not available", which); return CSP3_ERR_ARG; }
-        const std::vector<uint32_t> &v = sym->RL.words;
+        // the geometry CSP3_RL_W / CSP3_RL_NQ ask for, otherwise one warp per bundle (compiled here when not yet cached)
+        csp3_lu_symbolic &Sy = *const_cast<csp3_lu_symbolic *>(sym);
+        const RowlaneProgram *RLp;
+        { std::lock_guard<std::mutex> lock(Sy.rl_mu); RLp = rowlane_program(Sy, tuning().rl_warps > 0 ? kRlVariants - 1 : 0); }
+        if (!RLp) { set_error("lu_get_program: program %d not available", which); return CSP3_ERR_ARG; }
+        const RowlaneProgram &RL = *RLp;
+        const std::vector<uint32_t> &v = RL.words;
         if (geometry) {
             std::memset(geometry, 0, 8 * sizeof(int64_t));
-            geometry[0] = sym->RL.update_quads; geometry[1] = kRlStageQuads; geometry[2] = sym->RL.nslots; geometry[3] = sym->RL.late_quads;
-            geometry[4] = sym->RL.ops; geometry[5] = sym->RL.quads; geometry[6] = (i64)sym->RL.smem_bytes; geometry[7] = sym->RL.update_records;
+            geometry[0] = RL.update_quads; geometry[1] = RL.stage_quads | (RL.warps << 8); geometry[2] = RL.nslots; geometry[3] = RL.late_quads;
+            geometry[4] = RL.ops; geometry[5] = RL.quads; geometry[6] = (i64)RL.smem_bytes; geometry[7] = RL.update_records;
         }
         if (buf && capacity >= (int64_t)(v.size() * 4)) std::memcpy(buf, v.data(), v.size() * 4);
         return (int64_t)(v.size() * 4);
@@ -643,6 +693,7 @@ int csp3_lu_destroy(csp3_lu_symbolic *sym)
         if (!sym->dev[d].ready && !sym->stage[d].ready) continue;
         if (have) cudaSetDevice(d);
         if (sym->dev[d].arena) cudaFree(sym->dev[d].arena);
+        for (auto &R : sym->dev[d].rl) if (R.prog) cudaFree(R.prog);
         if (sym->stage[d].ready) free_stage(sym->stage[d]);
     }
     if (have) cudaSetDevice(cur);
@@ -677,7 +728,6 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
     const size_t i_wfs = add(sym->WF.prog.bytes.data(), wsolve ? sym->WF.prog.bytes.size() : 0);
     const size_t i_wbs = add(sym->WB.prog.bytes.data(), wsolve ? sym->WB.prog.bytes.size() : 0);
     const size_t i_prf = add(sym->PP.prog.bytes.data(), sym->PP.ok ? sym->PP.prog.bytes.size() : 0);
-    const size_t i_rl = add(sym->RL.words.data(), sym->RL.ok ? sym->RL.words.size() * 4 : 0);
     std::vector<uint8_t> ldiag(F.Li.size(), 0);
     for (i64 k = 0; k < sym->n; ++k) ldiag[(size_t)F.Lp[(size_t)k]] = 1;
     const size_t i_ldiag = add(ldiag.data(), ldiag.size());
@@ -726,11 +776,8 @@ int csp3_lu_upload(csp3_lu_symbolic *sym, void *stream)
         D.prf_prog = (const uint8_t *)at(i_prf); D.prf_prog_bytes = (i32)sym->PP.prog.bytes.size();
         D.prf_nslots = sym->PP.nslots; D.prf_lsrc = sym->PP.ring + sym->PP.landing; D.prf_steps = sym->PP.steps; D.prf_smem = sym->PP.smem_bytes;
     }
-    if (sym->RL.ok && sym->RL.smem_bytes <= (size_t)200 * 1024) {
-        D.rl_ok = true;
-        D.rl_prog = (const uint8_t *)at(i_rl);
-        D.rl_quads = sym->RL.quads; D.rl_nslots = sym->RL.nslots;
-    }
+    D.owner = sym; D.devid = devid;
+    D.rl_enabled = D.wide_ok && D.wide_S == 8 && D.wide_solve_ok;      // the sweeps that read 8-system bundles
     D.d_ldiag = (const uint8_t *)at(i_ldiag);
     D.ready = true;
     return 0;

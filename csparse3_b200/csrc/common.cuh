@@ -23,6 +23,9 @@ const char *get_error();
     } while (0)
 
 constexpr int kNumSMs = 148;   // B200
+// row-lane refactor program geometries (warps per bundle, quads per stage); the last one is the CSP3_RL_W / CSP3_RL_NQ override
+constexpr int kRlVariants = 5;
+constexpr int kRlGeometry[kRlVariants][2] = {{1, 3}, {2, 2}, {4, 2}, {8, 3}, {0, 0}};
 
 // ---- device copy of the LU schedule (one per device) ------------------------------------------------------
 struct DevSchedule {
@@ -52,9 +55,17 @@ struct DevSchedule {
     i32 prf_prog_bytes = 0, prf_nslots = 0, prf_steps = 0, prf_lsrc = 0;
     size_t prf_smem = 0;
     // row-lane refactor program (lu_rowlane.cu), bundles of 8 systems
-    bool rl_ok = false;
-    const uint8_t *rl_prog = nullptr;
-    i32 rl_quads = 0, rl_nslots = 0;
+    // (one program per geometry: warps per bundle x quads per stage, compiled and uploaded on first use)
+    struct RlVariant {
+        bool ok = false, tried = false;
+        uint8_t *prog = nullptr;           // own device allocation
+        i32 quads = 0, nslots = 0, warps = 1, stage_quads = 3, stream_off[8] = {};
+        size_t smem = 0;
+    };
+    mutable RlVariant rl[kRlVariants];
+    bool rl_enabled = false;               // the sweeps this kernel's factor layout needs are available
+    void *owner = nullptr;                 // csp3_lu_symbolic the schedule belongs to (lazy compilation of the variants)
+    int devid = 0;
     void *arena = nullptr;             // single allocation backing all of the above
     size_t arena_bytes = 0;
 };
@@ -77,6 +88,8 @@ int launch_growth(const DevSchedule &D, i64 batch, const double *Lw, double *gro
 int launch_refactor_panel(const DevSchedule &D, i64 batch, const double *Ax, double *Lw, double *Uw, i32 *status,
                           double *growth, cudaStream_t st);
 bool use_rowlane(const DevSchedule &D, i64 batch);
+int rowlane_variant(const DevSchedule &D, i64 batch);      // index into DevSchedule::rl, or -1: not the row-lane kernel
+int ensure_rowlane_variant(const DevSchedule &D, int variant);   // api.cu: compiles / uploads on first use; 0 when available
 int launch_refactor_rowlane(const DevSchedule &D, i64 batch, const double *Ax, double *Lw, double *Uw, i32 *status, cudaStream_t st);
 int launch_solve_wide(const DevSchedule &D, i64 batch, const double *Lw, const double *Uw, const double *b, double *x,
                       double *z1, double *z2, cudaStream_t st);
@@ -88,7 +101,7 @@ struct Tuning {
     int rf_S = 0, sv_S = 0, ws_S = 0, rf_win = 0, sv_stage = 0;
     int tmem = 0;                          // CSP3_TMEM=1: experimental refactor kernel with the accumulator in tensor memory (lu_refactor_tmem_kernel)
     int panel = 0, panel_fma = 0, panel_budget = 0;          // CSP3_PANEL=1 selects the experimental panel refactor kernel (lu_panel.cu), CSP3_PANEL_FMA (fused multiply-add, not bit-exact)
-    int rowlane = -1, rl_warps = 0;        // row-lane refactor kernel (lu_rowlane.cu): -1 automatic (patterns whose wide program leaves < 5 bundles per SM), CSP3_ROWLANE=0 / 1 never / always; CSP3_RL_WARPS bundles per CTA (1, 4)
+    int rowlane = -1, rl_warps = 0, rl_nq = 0;        // row-lane refactor kernel (lu_rowlane.cu): -1 automatic (patterns whose wide program leaves < 5 bundles per SM), CSP3_ROWLANE=0 / 1 never / always; CSP3_RL_W warps per bundle (1, 2, 4, 8), CSP3_RL_NQ quads per stage
     int wide = 1, wide_solve = 1, wide_S = 0, wide_R = 0, wide_ring = 0, wide_stage = 0, wide_budget = 0;   // CSP3_WIDE (0 disables), CSP3_WIDE_S/_R/_F/_BUDGET
 };
 Tuning &tuning();

@@ -434,15 +434,33 @@ bool use_panel(const DevSchedule &D, i64 batch)
     (void)batch;
     return D.panel_ok && tuning().panel != 0 && tuning().ws_S == 0 && (!D.wide_ok || D.wide_S == 8);
 }
+// Which refactor kernel serves `batch` systems on the workspace path (measured on B200):
+//  * the wide kernel is the throughput kernel: one warp per bundle, everything of a bundle in shared memory; best
+//    when the batch fills the GPU (config 3: 6.6 ms for 1,250 bundles) but a bundle is one sequential walk (4.7 ms
+//    whatever the batch), and patterns with long columns leave 3 bundles per SM (config 4);
+//  * the row-lane kernel runs 1 / 2 / 4 / 8 warps per bundle on different columns (9 KB of shared memory per warp):
+//    8 warps up to 64 bundles (config 3: 1.8 ms), 4 warps up to one wave of 3 bundles per SM (2.3 - 2.8 ms), 2 warps
+//    up to 6 bundles per SM (4.8 ms at 625 bundles against 5.3 ms), above that the wide kernel -- or, for the
+//    long-column patterns, one warp per bundle (config 4: 60.9 ms against 80.9 ms).
+int rowlane_variant(const DevSchedule &D, i64 batch)
+{
+    const Tuning &t = tuning();
+    if (!D.rl_enabled || t.rowlane == 0 || t.ws_S != 0) return -1;
+    if (t.rowlane < 0 && (t.tmem != 0 || t.panel != 0)) return -1;      // an experimental kernel was asked for explicitly
+    if (t.rl_warps > 0) return kRlVariants - 1;                       // CSP3_RL_W / CSP3_RL_NQ: forced geometry
+    const i64 bundles = (batch + 7) / 8;
+    const bool long_columns = D.wrf_smem > (size_t)40 * 1024;
+    if (bundles <= 64) return 3;
+    if (bundles <= (i64)3 * kNumSMs) return 2;
+    if (bundles <= (i64)6 * kNumSMs) return 1;
+    if (long_columns || t.rowlane > 0) return 0;
+    return -1;
+}
+
 bool use_rowlane(const DevSchedule &D, i64 batch)
 {
-    (void)batch;
-    if (!D.rl_ok || tuning().rowlane == 0 || tuning().ws_S != 0 || !D.wide_ok || D.wide_S != 8 || !D.wide_solve_ok) return false;
-    if (tuning().rowlane > 0) return true;                       // CSP3_ROWLANE=1: always
-    // automatic: the wide refactor keeps accumulator, L cache and landing area of a bundle in shared memory and is the
-    // faster kernel while >= 5 bundles per SM are resident (config 3: 24.8 KB, 6.6 ms against 9.7 ms); patterns with
-    // long columns leave 3 bundles per SM (config 4: 57 KB, 80.9 ms) where the row-lane kernel (9 KB) needs 60.9 ms
-    return D.wrf_smem > (size_t)40 * 1024;
+    const int v = rowlane_variant(D, batch);
+    return v >= 0 && ensure_rowlane_variant(D, v) == 0;
 }
 // (use_tmem: lu_wide.cu.  With the panel kernel selected the factors stay in 8-system bundles.)
 

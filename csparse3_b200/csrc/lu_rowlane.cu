@@ -73,7 +73,8 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct RowlaneArgs {
-    const uint8_t *prog;      // quads of 176 bytes, padded with END quads (rowlane_program.hpp)
+    const uint8_t *prog;      // quads of 304 bytes, one padded stream per warp of the bundle (rowlane_program.hpp)
+    i32 stream_off[kRlMaxWarps];   // first quad of every stream
     i32 nslots, nnzA, lnz, unz;
     i64 batch;
     const double *Ax;
@@ -109,22 +110,30 @@ __device__ __forceinline__ void load_multiplier(double2 &m, unsigned addr, unsig
                  : "+d"(m.x), "+d"(m.y) : "r"(addr), "r"(flag) : "memory");
 }
 
-// One pass of the main loop = one program stage of 3 quads (12 records).  All global loads of a warp share ONE
-// scoreboard slot (ptxas assigns every LDG to the same slot), so a wait for any load waits for all outstanding ones:
-// the operands of a WHOLE stage are requested at once, one stage before they are used.  Two register sets alternate:
-// at the top of a pass the set of this stage is complete (its loads are the only outstanding ones; one dummy use makes
-// the wait happen there), then the loads of the next stage are issued into the other set, then the quads execute.
-template <int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, 12 / WARPS) lu_refactor_rowlane_kernel(const RowlaneArgs a)
+// One pass of the main loop = one program stage of NQ quads.  All global loads of a warp share ONE scoreboard slot
+// (ptxas assigns every LDG to the same slot), so a wait for any load waits for all outstanding ones: the operands of a
+// WHOLE stage are requested at once, one stage before they are used.  Two register sets alternate: at the top of a pass
+// the set of this stage is complete (its loads are the only outstanding ones; one dummy use makes the wait happen
+// there), then the loads of the next stage are issued into the other set, then the quads execute.
+//
+// W warps of a CTA share a bundle: every warp runs its own stream of the program (its own columns, accumulator and
+// program ring).  A warp publishes the number of columns it has finished in shared memory at the top of a pass (no load
+// is outstanding there, so the fence in front of the flag is cheap) and reads the other warps' counters before it
+// requests the operands of a stage whose sources belong to them: ahead of time when they are already final, otherwise
+// when the stage is reached (everything before it has been executed and published by then: no deadlock).
+template <int W, int NQ>
+__global__ void __launch_bounds__(32 * W, (W == 2 && NQ == 1) ? 10 : 1) lu_refactor_rowlane_kernel(const RowlaneArgs a)
 {
-    constexpr int S = 8, NQ = kRlStageQuads, NR = kRlQuadRecords, SR = NQ * NR;
+    constexpr int S = 8, NR = kRlQuadRecords, SR = NQ * NR;
     constexpr unsigned QUAD_BYTES = kRlQuadWords * 4, STAGE_BYTES = NQ * QUAD_BYTES, RING_BYTES = kRlRingStages * STAGE_BYTES;
     static_assert(STAGE_BYTES % 16 == 0 && NR == 4, "geometry");
     extern __shared__ __align__(16) uint8_t smem_all[];
-    const int lane = threadIdx.x & 31, g = lane >> 2, h = lane & 3;
-    const i64 b = (i64)blockIdx.x * WARPS + (threadIdx.x >> 5);          // one warp per bundle, WARPS bundles per CTA
-    if (b * S >= a.batch) return;
-    uint8_t *smem_raw = smem_all + (size_t)(threadIdx.x >> 5) * ((size_t)a.nslots * 64u + RING_BYTES);
+    const int lane = threadIdx.x & 31, g = lane >> 2, h = lane & 3, wid = threadIdx.x >> 5;
+    const i64 b = blockIdx.x;                                            // one bundle per CTA
+    // shared memory: [0, 16) progress counters (8 x 16 bits), [64, 64 + 8 * W * 4) failure codes, then per warp accumulator + ring
+    const unsigned flags_s = (unsigned)__cvta_generic_to_shared(smem_all);
+    int *fails = reinterpret_cast<int *>(smem_all + 64);
+    uint8_t *smem_raw = smem_all + 64 + 32 * kRlMaxWarps + (size_t)wid * ((size_t)a.nslots * 64u + RING_BYTES);
     const i64 sys0 = b * S + 2 * h, sys1 = sys0 + 1;
     const char *Axs0 = reinterpret_cast<const char *>(a.Ax + (sys0 < a.batch ? sys0 : a.batch - 1) * a.nnzA);
     const char *Axs1 = reinterpret_cast<const char *>(a.Ax + (sys1 < a.batch ? sys1 : a.batch - 1) * a.nnzA);
@@ -136,10 +145,14 @@ __global__ void __launch_bounds__(32 * WARPS, 12 / WARPS) lu_refactor_rowlane_ke
     const unsigned lw_off = 48u + (unsigned)g * 16u;                     // this lane group's four lane words inside a quad
     const unsigned aw_off = 176u + (unsigned)g * 16u;                    // ... and its four address words
     for (int t = lane; t < a.nslots * S; t += 32) reinterpret_cast<double *>(smem_raw)[t] = 0.0;
+    if (W > 1) {
+        if (threadIdx.x < 4) reinterpret_cast<unsigned *>(smem_all)[threadIdx.x] = 0u;
+        __syncthreads();
+    }
 
     // program ring: stage s lives in ring slot s % 4.  Three stages are loaded up front; entering stage s requests
     // stage s + 3 (into the slot stage s - 1 has left) and waits until at most that one group is pending.
-    const uint8_t *pnext = a.prog + lane * 16;
+    const uint8_t *pnext = a.prog + (size_t)a.stream_off[wid] * QUAD_BYTES + lane * 16;
     unsigned pdst = 0;
     auto request_stage = [&]() {
 #pragma unroll
@@ -155,7 +168,7 @@ __global__ void __launch_bounds__(32 * WARPS, 12 / WARPS) lu_refactor_rowlane_ke
 
     double2 Q0[SR], Q1[SR];
     const double2 zero2 = make_double2(0.0, 0.0);
-    // request the operands of the four quads of the stage at ring address sb
+    // request the operands of the quads of the stage at ring address sb
     auto request_operands = [&](unsigned sb, double2 (&Q)[SR]) {
 #pragma unroll
         for (int qd = 0; qd < NQ; ++qd) {
@@ -178,14 +191,30 @@ __global__ void __launch_bounds__(32 * WARPS, 12 / WARPS) lu_refactor_rowlane_ke
             }
         }
     };
+    // have the other warps finished the columns the stage at ring address sb reads?  (8 x 16-bit counters)
+    auto sources_final = [&](unsigned sb) -> bool {
+        const uint4 req = lds_u4(sb + 32);
+        uint4 done;
+        asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(done.x), "=r"(done.y), "=r"(done.z), "=r"(done.w) : "r"(flags_s) : "memory");
+        return (__vcmpgeu2(done.x, req.x) & __vcmpgeu2(done.y, req.y) & __vcmpgeu2(done.z, req.z) & __vcmpgeu2(done.w, req.w)) == 0xffffffffu;
+    };
     unsigned sb0 = ring_s, sb1 = ring_s + STAGE_BYTES;                   // ring addresses of this stage and the next
 #pragma unroll
     for (int d = 0; d < SR; ++d) { Q0[d] = zero2; Q1[d] = zero2; }
-    request_operands(sb0, Q0);
+    bool have0 = W == 1 || sources_final(sb0), have1 = false;            // operands of the stage already requested?
+    if (have0) request_operands(sb0, Q0);
 
     double2 m = zero2, piv = make_double2(1.0, 1.0), rcp = piv;
     int fail0 = INT32_MAX, fail1 = INT32_MAX;
-    unsigned sink = 0;
+    unsigned sink = 0, cols_done = 0, cols_published = 0;
+    auto publish = [&]() {
+        if (W > 1 && cols_done != cols_published) {
+            __threadfence_block();                 // this warp's L stores before the counter (no load is outstanding here)
+            __syncwarp();
+            if (lane == 0) asm volatile("st.volatile.shared.u16 [%0], %1;" ::"r"(flags_s + 2u * (unsigned)wid), "h"((unsigned short)cols_done) : "memory");
+            cols_published = cols_done;
+        }
+    };
     auto pivot_prologue = [&](const uint4 &h0) {
         piv = lds_d2(accb + (h0.y & 0xffffu));
         rcp = make_double2(rcp_refined(piv.x), rcp_refined(piv.y));
@@ -208,15 +237,31 @@ __global__ void __launch_bounds__(32 * WARPS, 12 / WARPS) lu_refactor_rowlane_ke
             stg_cs_d2(Ub + (size_t)(base + f_off64(w)), x);
         }
     };
-    // one stage: operands of this stage in C (requested one pass ago), the next stage's go to Q.  false: END reached
-    auto pass = [&](double2 (&C)[SR], double2 (&Q)[SR]) -> bool {
+    // one stage: operands of this stage in C (requested one pass ago when haveC), the next stage's go to Q.  false: END reached
+    auto pass = [&](double2 (&C)[SR], double2 (&Q)[SR], bool &haveC, bool &haveQ) -> bool {
         request_stage();
         cp_async_wait<1>();
         __syncwarp();                        // also: L values stored by other lanes are visible to the loads below
         // every global load of the warp is on one scoreboard slot: this use waits for the loads of C, which are the only
         // ones outstanding, BEFORE the loads of the next stage are issued; the quads below then never wait for memory
         sink ^= (unsigned)__double2hiint(C[0].x);
-        request_operands(sb1, Q);
+        if (W > 1) {
+            publish();
+            if (!haveC) {
+                // sources of other warps were not final a pass ago: everything before this stage is executed and
+                // published, so waiting here cannot deadlock; then read the operands now
+                unsigned spins = 0;
+                while (!sources_final(sb0))
+                    if (++spins > (1u << 26)) { fail0 = fail1 = -2; break; }      // a broken program must not hang the GPU
+                __threadfence_block();
+                request_operands(sb0, C);
+                sink ^= (unsigned)__double2hiint(C[0].x);
+            }
+            haveQ = sources_final(sb1);
+            if (haveQ) { __threadfence_block(); request_operands(sb1, Q); }
+        } else {
+            request_operands(sb1, Q);
+        }
 #pragma unroll
         for (int qd = 0; qd < NQ; ++qd) {
             const unsigned qa = sb0 + qd * QUAD_BYTES;
@@ -234,7 +279,7 @@ __global__ void __launch_bounds__(32 * WARPS, 12 / WARPS) lu_refactor_rowlane_ke
                 continue;
             }
             if (kind == (unsigned)kRlUpdLate) {
-                // rare: a source column was finalised less than two stages ago, read the operands now
+                // rare: a source column of this warp was finalised less than two stages ago, read the operands now
                 const uint4 aw = lds_u4(qa + aw_off);
                 __syncwarp();
                 double2 l[NR];
@@ -265,7 +310,8 @@ __global__ void __launch_bounds__(32 * WARPS, 12 / WARPS) lu_refactor_rowlane_ke
                         sts_d2(accb + f_slot64(w), c);
                     }
                 }
-            } else if (kind == (unsigned)kRlEnd) {
+                if (kind == (unsigned)kRlFin) ++cols_done;
+            } else {
                 return false;
             }
         }
@@ -275,20 +321,36 @@ __global__ void __launch_bounds__(32 * WARPS, 12 / WARPS) lu_refactor_rowlane_ke
     };
 #pragma unroll 1
     for (;;) {
-        if (!pass(Q0, Q1)) break;
-        if (!pass(Q1, Q0)) break;
+        if (!pass(Q0, Q1, have0, have1)) break;
+        if (!pass(Q1, Q0, have1, have0)) break;
     }
     cp_async_wait<0>();
+    publish();
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) {
         fail0 = min(fail0, __shfl_xor_sync(0xffffffffu, fail0, o));
         fail1 = min(fail1, __shfl_xor_sync(0xffffffffu, fail1, o));
     }
-    if (g == 0 && a.status != nullptr) {
+    if (W > 1) {
+        if (g == 0) { fails[(wid * 4 + h) * 2] = fail0; fails[(wid * 4 + h) * 2 + 1] = fail1; }
+        __syncthreads();
+        if (wid == 0 && g == 0)
+            for (int v = 1; v < W; ++v) { fail0 = min(fail0, fails[(v * 4 + h) * 2]); fail1 = min(fail1, fails[(v * 4 + h) * 2 + 1]); }
+    }
+    if (wid == 0 && g == 0 && a.status != nullptr) {
         if (sys0 < a.batch) a.status[sys0] = (fail0 == INT32_MAX) ? 0 : fail0;
         if (sys1 < a.batch) a.status[sys1] = (fail1 == INT32_MAX) ? 0 : fail1;
         if (sink == 0x7ff7dead && a.nslots < 0) a.status[0] = (i32)sink;          // keeps the dummy uses alive (never true)
     }
+}
+
+template <int W, int NQ>
+int launch_T(const RowlaneArgs &a, i64 grid, size_t smem, cudaStream_t st)
+{
+    CSP3_CUDA(cudaFuncSetAttribute(lu_refactor_rowlane_kernel<W, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lu_refactor_rowlane_kernel<W, NQ><<<(unsigned)grid, 32 * W, smem, st>>>(a);
+    CSP3_CUDA(cudaGetLastError());
+    return 0;
 }
 
 }  // namespace
@@ -296,23 +358,27 @@ __global__ void __launch_bounds__(32 * WARPS, 12 / WARPS) lu_refactor_rowlane_ke
 int launch_refactor_rowlane(const DevSchedule &D, i64 batch, const double *Ax, double *Lw, double *Uw, i32 *status, cudaStream_t st)
 {
     if (batch <= 0) return 0;
-    if (!D.rl_ok) { set_error("row-lane refactor program not available for this pattern"); return -1; }
+    const int v = rowlane_variant(D, batch);
+    if (v < 0 || ensure_rowlane_variant(D, v) != 0) { set_error("row-lane refactor program not available for this pattern"); return -1; }
+    const DevSchedule::RlVariant &R = D.rl[v];
     RowlaneArgs a;
-    a.prog = D.rl_prog;
-    a.nslots = D.rl_nslots; a.nnzA = D.nnzA; a.lnz = D.lnz; a.unz = D.unz;
+    a.prog = R.prog;
+    for (int w = 0; w < kRlMaxWarps; ++w) a.stream_off[w] = R.stream_off[w];
+    a.nslots = R.nslots; a.nnzA = D.nnzA; a.lnz = D.lnz; a.unz = D.unz;
     a.batch = batch; a.Ax = Ax; a.Lw = Lw; a.Uw = Uw; a.status = status;
     const i64 grid = (batch + 7) / 8;
-    const size_t smem = (size_t)D.rl_nslots * 64 + (size_t)kRlRingStages * kRlStageQuads * kRlQuadWords * 4;
-    const int warps = tuning().rl_warps == 4 ? 4 : 1;
-    if (warps == 4) {
-        CSP3_CUDA(cudaFuncSetAttribute(lu_refactor_rowlane_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * smem)));
-        lu_refactor_rowlane_kernel<4><<<(unsigned)((grid + 3) / 4), 128, 4 * smem, st>>>(a);
-    } else {
-        CSP3_CUDA(cudaFuncSetAttribute(lu_refactor_rowlane_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        lu_refactor_rowlane_kernel<1><<<(unsigned)grid, 32, smem, st>>>(a);
+    const size_t smem = R.smem;
+    switch (R.warps * 8 + R.stage_quads) {
+        case 1 * 8 + 3: return launch_T<1, 3>(a, grid, smem, st);
+        case 2 * 8 + 1: return launch_T<2, 1>(a, grid, smem, st);
+        case 2 * 8 + 2: return launch_T<2, 2>(a, grid, smem, st);
+        case 4 * 8 + 2: return launch_T<4, 2>(a, grid, smem, st);
+        case 4 * 8 + 3: return launch_T<4, 3>(a, grid, smem, st);
+        case 8 * 8 + 3: return launch_T<8, 3>(a, grid, smem, st);
+        default: break;
     }
-    CSP3_CUDA(cudaGetLastError());
-    return 0;
+    set_error("row-lane refactor: no kernel for %d warps per bundle and %d quads per stage", R.warps, R.stage_quads);
+    return -1;
 }
 
 }  // namespace csp3

@@ -84,18 +84,20 @@ struct Quad {
 
 }  // namespace
 
-bool compile_rowlane_refactor(i64 n64, const i32 *Ap, const std::vector<i32> &q, const Factor &F, const Schedule &S,
-                              RowlaneProgram &P, const char **why)
+bool compile_rowlane_refactor(i64 n64, const i32 *Ap, const std::vector<i32> &q, const Factor &F, const Schedule &S, i32 warps,
+                              i32 stage_quads, RowlaneProgram &P, const char **why)
 {
     P = RowlaneProgram();
     const i32 n = (i32)n64;
     if (n <= 0) { *why = "empty matrix"; return false; }
+    if (warps < 1 || warps > kRlMaxWarps || stage_quads < 1 || stage_quads > 4) { *why = "row-lane program: bad geometry"; return false; }
     const std::vector<i32> &Lp = F.Lp, &Up = F.Up, &Ui = F.Ui;
     if ((i64)Lp[n] >= (1ll << 26) || (i64)Up[n] >= (1ll << 26) || (i64)Ap[n] >= (1ll << 29)) {
         *why = "row-lane program: factor too large for 32-bit byte offsets";
         return false;
     }
     if (S.max_col_len > kRlMaxSlots) { *why = "row-lane program: column longer than 1024 entries"; return false; }
+    if (warps > 1 && n > 65000 * warps) { *why = "row-lane program: too many columns per warp for 16-bit progress counters"; return false; }
     for (i32 k = 0; k < n; ++k) {
         const i32 col = q.empty() ? k : q[k];
         if (S.cols[k].ucnt > kRlMaxOff || S.cols[k].lcnt > kRlMaxOff || Ap[col + 1] - Ap[col] > kRlMaxOff) {
@@ -103,7 +105,9 @@ bool compile_rowlane_refactor(i64 n64, const i32 *Ap, const std::vector<i32> &q,
             return false;
         }
     }
+    P.warps = warps; P.stage_quads = stage_quads;
     P.nslots = (std::max(S.max_col_len, 1) + 1) & ~1;
+    const i64 NQ = stage_quads;
 
     // users of every column (columns k with U(j,k) != 0) and the count of unfinished sources
     std::vector<i32> uptr((size_t)n + 1, 0), users, ndeps((size_t)n, 0);
@@ -118,15 +122,25 @@ bool compile_rowlane_refactor(i64 n64, const i32 *Ap, const std::vector<i32> &q,
     }
     std::set<i32> ready;
     for (i32 k = 0; k < n; ++k) if (ndeps[k] == 0) ready.insert(k);
-    std::vector<i64> stored_stage((size_t)n, 1ll << 40);         // stage whose execution finalises L(:,k)
     const int window = getenv("CSP3_RL_WINDOW") ? std::max(1, atoi(getenv("CSP3_RL_WINDOW"))) : 48;
+    const i64 margin = getenv("CSP3_RL_MARGIN") ? atoi(getenv("CSP3_RL_MARGIN")) : 2 * NQ;      // quads of slack for a cross-warp source
 
-    std::vector<Quad> quads;
-    bool have_fin = false;
-    Quad fin;
-    auto stage_of = [](i64 quad) { return quad / kRlStageQuads; };
+    // one stream of quads per warp of the bundle; a column lives on one warp (its accumulator is that warp's)
+    struct Stream {
+        std::vector<Quad> quads;
+        bool have_fin = false;
+        Quad fin;
+        i32 ncols = 0;
+        std::vector<std::array<uint16_t, kRlMaxWarps>> req;       // per stage: columns the other warps must have finished
+        i64 clock() const { return (i64)quads.size() + (have_fin ? 1 : 0); }
+    };
+    std::vector<Stream> st((size_t)warps);
+    std::vector<i32> owner((size_t)n, 0), colseq((size_t)n, 0);
+    std::vector<i64> stored_stage((size_t)n, 1ll << 40);         // stage (of the owner's stream) whose execution finalises L(:,k)
+    std::vector<i64> finish_clock((size_t)n, 1ll << 40);          // owner's quad count when the column is finalised (time proxy)
+    auto stage_of = [NQ](i64 quad) { return quad / NQ; };
     // homogeneous quads of `recs[from, to)`, one base for all records
-    auto emit_role4 = [&](int kind, const std::vector<Rec> &recs, size_t from, size_t to, uint32_t base, bool &first_store, i32 pivot_slot, i32 k) {
+    auto emit_role4 = [&](Stream &T, int kind, const std::vector<Rec> &recs, size_t from, size_t to, uint32_t base, bool &first_store, i32 pivot_slot, i32 k) {
         for (size_t r0 = from; r0 < to; r0 += kRlQuadRecords) {
             Quad Q;
             const size_t cnt = std::min<size_t>(kRlQuadRecords, to - r0);
@@ -138,59 +152,68 @@ bool compile_rowlane_refactor(i64 n64, const i32 *Ap, const std::vector<i32> &q,
                 Q.w[0] |= (uint32_t)(kind == kRlStoreL4 ? kRlRoleL : kind == kRlStoreU4 ? kRlRoleU : kRlRoleA) << (24 + 2 * r);
             }
             if (kind != kRlLoad4 && first_store) { Q.w[0] |= kRlFlagP; Q.mslot(0, pivot_slot); Q.w[3] = (uint32_t)k + 1u; first_store = false; }
-            quads.push_back(Q);
+            T.quads.push_back(Q);
         }
     };
     struct URec { Rec w; bool isnew; i32 mslot; uint32_t base; i32 j; };
     std::vector<Op> ops;
     std::vector<Rec> recs;
     std::vector<URec> urecs;
-    // update quads of column k that would read late if its first update quad were quad `pos`
-    auto late_cost = [&](i32 k, i64 pos) {
+    // update quads of column k that would stall if it were eliminated next on warp w: a source of the same warp finalised
+    // less than two stages before (late read), or a source of another warp that is finalised about then (wait)
+    auto stall_cost = [&](i32 k, i32 w) {
+        const Stream &T = st[(size_t)w];
         const ColDesc &cd = S.cols[k];
-        i64 rec = 0, late = 0, last_late_quad = -1;
+        const i64 a_recs = (cd.a_cnt + kRlOps - 1) / kRlOps;
+        const i64 load4 = T.have_fin ? (std::max<i64>(a_recs, 1) - 1 + kRlQuadRecords - 1) / kRlQuadRecords : (a_recs + kRlQuadRecords - 1) / kRlQuadRecords;
+        const i64 pos = T.clock() + load4;
+        i64 rec = 0, cost = 0, last_quad = -1;
         for (i32 t = 0; t < cd.pair_cnt; ++t) {
             const PairDesc &pd = S.pairs[(size_t)cd.pair_ptr + t];
             const i32 j = Ui[Up[k] + t];
             const i64 nrec = (pd.llen + kRlOps - 1) / kRlOps;
             for (i64 r = 0; r < nrec; ++r, ++rec) {
                 const i64 qd = pos + rec / kRlQuadRecords;
-                if (qd != last_late_quad && stored_stage[j] > stage_of(qd) - 2) { ++late; last_late_quad = qd; }
+                if (qd == last_quad) continue;
+                const bool stall = owner[j] == w ? stored_stage[j] > stage_of(qd) - 2 : finish_clock[j] + margin > qd;
+                if (stall) { ++cost; last_quad = qd; }
             }
         }
-        return late;
+        return cost;
     };
     P.order.reserve((size_t)n);
     for (i32 done = 0; done < n; ++done) {
         if (ready.empty()) { *why = "row-lane program: dependency cycle (internal error)"; return false; }
+        // the warp that is free first (fewest quads so far) takes the next column
+        i32 w = 0;
+        for (i32 v = 1; v < warps; ++v) if (st[(size_t)v].clock() < st[(size_t)w].clock()) w = v;
         i32 best = -1;
         i64 best_cost = 0;
         int seen = 0;
         for (auto it = ready.begin(); it != ready.end() && seen < window; ++it, ++seen) {
-            const ColDesc &cd = S.cols[*it];
-            const i64 a_recs = (cd.a_cnt + kRlOps - 1) / kRlOps;
-            const i64 load4 = have_fin ? (std::max<i64>(a_recs, 1) - 1 + kRlQuadRecords - 1) / kRlQuadRecords : (a_recs + kRlQuadRecords - 1) / kRlQuadRecords;
-            const i64 c = late_cost(*it, (i64)quads.size() + (have_fin ? 1 : 0) + load4);
+            const i64 c = stall_cost(*it, w);
             if (best < 0 || c < best_cost) { best = *it; best_cost = c; }
             if (c == 0) break;
         }
         const i32 k = best;
         ready.erase(k);
         P.order.push_back(k);
+        Stream &T = st[(size_t)w];
+        owner[k] = w; colseq[k] = T.ncols++;
         const ColDesc &cd = S.cols[k];
         const i32 col = q.empty() ? k : q[k];
         bool unused = false;
-        // ---- A(:,q[k]): the first record rides in the FIN quad of the previous column ------------------------------
+        // ---- A(:,q[k]): the first record rides in the FIN quad of the warp's previous column -----------------------
         ops.clear(); recs.clear();
         for (i32 t = 0; t < cd.a_cnt; ++t) ops.push_back({(i32)S.a_off[(size_t)cd.a_ptr + t], S.a_src[(size_t)cd.a_ptr + t] - Ap[col]});
         arrange(ops, recs, P.conflict_pairs);
         size_t from = 0;
-        if (have_fin) {
-            if (!recs.empty()) { fin.w[0] |= kRlHasA | ((uint32_t)kRlRoleA << 28); fin.rec(2, recs[0]); fin.base(2, (uint32_t)Ap[col] * 8u); fin.addr(2, (uint32_t)Ap[col] * 8u, 8); from = 1; }
-            quads.push_back(fin);
-            have_fin = false;
+        if (T.have_fin) {
+            if (!recs.empty()) { T.fin.w[0] |= kRlHasA | ((uint32_t)kRlRoleA << 28); T.fin.rec(2, recs[0]); T.fin.base(2, (uint32_t)Ap[col] * 8u); T.fin.addr(2, (uint32_t)Ap[col] * 8u, 8); from = 1; }
+            T.quads.push_back(T.fin);
+            T.have_fin = false;
         }
-        emit_role4(kRlLoad4, recs, from, recs.size(), (uint32_t)Ap[col] * 8u, unused, 0, k);
+        emit_role4(T, kRlLoad4, recs, from, recs.size(), (uint32_t)Ap[col] * 8u, unused, 0, k);
         // ---- UPDATE, one source column after the other in the stored order of U(:,k) ------------------------------
         urecs.clear();
         for (i32 t = 0; t < cd.pair_cnt; ++t) {
@@ -206,18 +229,36 @@ bool compile_rowlane_refactor(i64 n64, const i32 *Ap, const std::vector<i32> &q,
         P.update_records += (i64)urecs.size();
         for (size_t r0 = 0; r0 < urecs.size(); r0 += kRlQuadRecords) {
             Quad Q;
-            const i64 st = stage_of((i64)quads.size());
+            // A warp waits for the cross-warp sources of a WHOLE stage before it executes the stage: a column this warp
+            // finalises earlier in the same stage could be what the other warp is waiting for.  Such a quad starts a new stage.
+            bool cross = false;
+            for (size_t r = r0; r < std::min(urecs.size(), r0 + kRlQuadRecords); ++r) cross = cross || owner[urecs[r].j] != w;
+            if (cross) {
+                const size_t first = (size_t)(stage_of((i64)T.quads.size()) * NQ);
+                bool fin_before = false;
+                for (size_t t = first; t < T.quads.size(); ++t) fin_before = fin_before || (T.quads[t].w[0] & 7u) == (uint32_t)kRlFin;
+                if (fin_before) { while (T.quads.size() % (size_t)NQ != 0) { T.quads.push_back(Quad()); ++P.pad_quads; } }
+            }
+            const i64 stg = stage_of((i64)T.quads.size());
+            if ((i64)T.req.size() <= stg) T.req.resize((size_t)stg + 1, std::array<uint16_t, kRlMaxWarps>{});
             bool late = false;
             for (size_t r = r0; r < std::min(urecs.size(), r0 + kRlQuadRecords); ++r) {
                 const URec &u = urecs[r];
                 const int ri = (int)(r - r0);
                 Q.rec(ri, u.w); Q.base(ri, u.base); Q.mslot(ri, u.mslot); Q.addr(ri, u.base, 64);
                 if (u.isnew) Q.w[0] |= 0x100u << ri;
-                if (stored_stage[u.j] > st) { *why = "row-lane program: source column not finalised (internal error)"; return false; }
-                late = late || stored_stage[u.j] > st - 2;
+                if (owner[u.j] == w) {
+                    if (stored_stage[u.j] > stg) { *why = "row-lane program: source column not finalised (internal error)"; return false; }
+                    late = late || stored_stage[u.j] > stg - 2;
+                } else {
+                    // a source of another warp: that warp must have finished colseq + 1 columns before this stage's operands are read
+                    uint16_t &rq = T.req[(size_t)stg][(size_t)owner[u.j]];
+                    rq = std::max<uint16_t>(rq, (uint16_t)(colseq[u.j] + 1));
+                    ++P.cross_records;
+                }
             }
             Q.kind(late ? kRlUpdLate : kRlUpdate);
-            quads.push_back(Q);
+            T.quads.push_back(Q);
             ++P.update_quads;
             if (late) ++P.late_quads;
         }
@@ -231,27 +272,38 @@ bool compile_rowlane_refactor(i64 n64, const i32 *Ap, const std::vector<i32> &q,
         ops.clear();
         for (i32 t = 0; t < cd.ucnt; ++t) ops.push_back({t, t});
         arrange(ops, urecs2, P.conflict_pairs);
-        if (lrecs.size() > 1) emit_role4(kRlStoreL4, lrecs, 0, lrecs.size() - 1, (uint32_t)(cd.lp + 1) * 64u, first_store, pivot_slot, k);
-        if (urecs2.size() > 1) emit_role4(kRlStoreU4, urecs2, 0, urecs2.size() - 1, (uint32_t)cd.up * 64u, first_store, pivot_slot, k);
-        fin = Quad();
-        fin.kind(kRlFin);
-        if (!lrecs.empty()) { fin.w[0] |= kRlHasL | ((uint32_t)kRlRoleL << 24); fin.rec(0, lrecs.back()); fin.base(0, (uint32_t)(cd.lp + 1) * 64u); }
-        if (!urecs2.empty()) { fin.w[0] |= kRlHasU | ((uint32_t)kRlRoleU << 26); fin.rec(1, urecs2.back()); fin.base(1, (uint32_t)cd.up * 64u); }
-        if (first_store) { fin.w[0] |= kRlFlagP; fin.mslot(0, pivot_slot); fin.w[3] = (uint32_t)k + 1u; }
-        have_fin = true;
-        stored_stage[k] = stage_of((i64)quads.size());          // the FIN quad is the next quad emitted
+        if (lrecs.size() > 1) emit_role4(T, kRlStoreL4, lrecs, 0, lrecs.size() - 1, (uint32_t)(cd.lp + 1) * 64u, first_store, pivot_slot, k);
+        if (urecs2.size() > 1) emit_role4(T, kRlStoreU4, urecs2, 0, urecs2.size() - 1, (uint32_t)cd.up * 64u, first_store, pivot_slot, k);
+        T.fin = Quad();
+        T.fin.kind(kRlFin);
+        if (!lrecs.empty()) { T.fin.w[0] |= kRlHasL | ((uint32_t)kRlRoleL << 24); T.fin.rec(0, lrecs.back()); T.fin.base(0, (uint32_t)(cd.lp + 1) * 64u); }
+        if (!urecs2.empty()) { T.fin.w[0] |= kRlHasU | ((uint32_t)kRlRoleU << 26); T.fin.rec(1, urecs2.back()); T.fin.base(1, (uint32_t)cd.up * 64u); }
+        if (first_store) { T.fin.w[0] |= kRlFlagP; T.fin.mslot(0, pivot_slot); T.fin.w[3] = (uint32_t)k + 1u; }
+        T.have_fin = true;
+        stored_stage[k] = stage_of((i64)T.quads.size());         // the FIN quad is the next quad this warp emits
+        finish_clock[k] = T.clock();
         for (i32 p = uptr[k]; p < uptr[(size_t)k + 1]; ++p)
             if (--ndeps[users[(size_t)p]] == 0) ready.insert(users[(size_t)p]);
     }
-    if (have_fin) quads.push_back(fin);
-    P.quads = (i32)quads.size();
-    const size_t padded = (quads.size() + kRlStageQuads) / kRlStageQuads * kRlStageQuads + 4 * kRlStageQuads;
     Quad endq;
     endq.kind(kRlEnd);
-    while (quads.size() < padded) quads.push_back(endq);
-    P.words.resize(quads.size() * kRlQuadWords);
-    for (size_t i = 0; i < quads.size(); ++i) std::copy(quads[i].w, quads[i].w + kRlQuadWords, P.words.begin() + i * kRlQuadWords);
-    P.smem_bytes = (size_t)P.nslots * 64 + (size_t)kRlRingStages * kRlStageQuads * kRlQuadWords * 4;
+    P.quads = 0;
+    for (i32 w = 0; w < warps; ++w) {
+        Stream &T = st[(size_t)w];
+        if (T.have_fin) T.quads.push_back(T.fin);
+        P.stream_quads[w] = (i32)T.quads.size();
+        P.quads += (i32)T.quads.size();
+        const size_t padded = (T.quads.size() + (size_t)NQ) / (size_t)NQ * (size_t)NQ + 4 * (size_t)NQ;
+        while (T.quads.size() < padded) T.quads.push_back(endq);
+        // cross-warp requirements of a stage ride in the spare header words of its first quad (8 x 16 bits)
+        for (size_t sg = 0; sg < T.req.size(); ++sg)
+            for (int v = 0; v < kRlMaxWarps; ++v) T.quads[sg * (size_t)NQ].w[8 + v / 2] |= (uint32_t)T.req[sg][(size_t)v] << (16 * (v & 1));
+        P.stream_off[w] = (i64)P.words.size() / kRlQuadWords;
+        const size_t base = P.words.size();
+        P.words.resize(base + T.quads.size() * kRlQuadWords);
+        for (size_t i = 0; i < T.quads.size(); ++i) std::copy(T.quads[i].w, T.quads[i].w + kRlQuadWords, P.words.begin() + base + i * kRlQuadWords);
+    }
+    P.smem_bytes = (size_t)warps * ((size_t)P.nslots * 64 + (size_t)kRlRingStages * (size_t)NQ * kRlQuadWords * 4) + 64 + 32 * kRlMaxWarps;
     P.ok = true;
     return true;
 }

@@ -6,7 +6,10 @@
 // read what this kernel writes).  Only the accumulator of the column being eliminated lives in shared memory (`nslots`
 // entries of 64 bytes); L operands and A values go from global memory (L1 / L2 / HBM) straight to registers.
 //
-// Program = STAGES of 3 QUADS of 4 RECORDS of 8 lane words.  A quad is homogeneous (one kind), so the kernel
+// Program = one STREAM per warp of the bundle (1, 2, 4 or 8 warps eliminate different columns at the same time, each
+// in its own accumulator; a column's sources may belong to other warps: the first quad of a stage carries, per other
+// warp, how many columns that warp must have finished before the stage's operands may be read).  A stream = STAGES of
+// `stage_quads` QUADS of 4 RECORDS of 8 lane words.  A quad is homogeneous (one kind), so the kernel
 // dispatches once per quad and runs straight-line, predicated code for its records.  All global loads of a warp share
 // one scoreboard slot, so the operands of a WHOLE stage (12 records) are requested together, one stage ahead; the
 // program itself is copied with cp.async into a shared-memory ring, three stages ahead.
@@ -34,7 +37,7 @@
 //   h0.y    mslot[0] * 64 | mslot[1] * 64 << 16        h0.z   mslot[2] * 64 | mslot[3] * 64 << 16
 //   h0.w    P: k + 1
 //   h1      base[0..3]: byte offsets (L / U array of the bundle, or a system's Ax)
-//   h2      spare
+//   h2      first quad of a stage: 8 x 16 bits, columns warp v of the bundle must have finished (0: no requirement)
 //   lane words [g][record] (a lane group reads its four words with one 16-byte access): bit 31 valid, bits 16-30 off
 //           (entries relative to base), bits 6-15 slot * 64 (an empty lane group repeats its partner's slot)
 //   address words [g][record]: byte offset of the operand the record reads from global memory (base + off, scaled:
@@ -55,20 +58,26 @@ constexpr int kRlMaxSlots = 1024;      // accumulator slots (slot * 64 is a 16-b
 constexpr int kRlMaxOff = 32767;       // relative entry offset of a lane word
 constexpr int kRlQuadRecords = 4;
 constexpr int kRlQuadWords = 12 + 2 * kRlQuadRecords * kRlOps;  // 76
-constexpr int kRlStageQuads = 3;       // 912 bytes: 57 cp.async pieces of 16 bytes (two operand register sets of 12 records fit 168 registers)
 constexpr int kRlRingStages = 4;
+constexpr int kRlMaxWarps = 8;         // warps of a bundle (each eliminates its own columns in its own accumulator)
 
 struct RowlaneProgram {
     bool ok = false;
-    i32 nslots = 0;                    // accumulator entries
-    i32 quads = 0;                     // without the END padding
+    i32 warps = 1;                     // warps per bundle = streams of the program
+    i32 stage_quads = 3;               // quads per stage (operands of a stage are requested together, one stage ahead)
+    i32 nslots = 0;                    // accumulator entries (per warp)
+    i32 quads = 0;                     // all streams, without the END padding
+    i32 stream_quads[kRlMaxWarps] = {};   // quads of every stream (without padding)
+    i64 stream_off[kRlMaxWarps] = {};     // first quad of every stream in `words`
+    i64 cross_records = 0;             // update records whose source column belongs to another warp
+    i64 pad_quads = 0;                 // empty quads (a quad with cross-warp sources never shares a stage with an earlier FIN)
     size_t smem_bytes = 0;
     std::vector<uint32_t> words;       // 76 words per quad (quads + padding)
     i64 ops = 0, update_records = 0, update_quads = 0, late_quads = 0, conflict_pairs = 0;
     std::vector<i32> order;            // elimination order of the columns
 };
 
-bool compile_rowlane_refactor(i64 n, const i32 *Ap, const std::vector<i32> &q, const Factor &F, const Schedule &S,
-                              RowlaneProgram &P, const char **why);
+bool compile_rowlane_refactor(i64 n, const i32 *Ap, const std::vector<i32> &q, const Factor &F, const Schedule &S, i32 warps,
+                              i32 stage_quads, RowlaneProgram &P, const char **why);
 
 }  // namespace csp3

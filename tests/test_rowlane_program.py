@@ -74,13 +74,14 @@ def test_rowlane_program_reports_bad_pivots():
     assert fail.tolist() == [0, 3, 3]
 
 
-@pytest.mark.parametrize("env", [
-{"CSP3_RL_WINDOW": "1"}, {"CSP3_RL_WINDOW": "4"}])
+@pytest.mark.parametrize("env", [{"CSP3_RL_WINDOW": "1"}, {"CSP3_RL_WINDOW": "4"}, {"CSP3_RL_W": "2", "CSP3_RL_NQ": "1"},
+                                 {"CSP3_RL_W": "4", "CSP3_RL_NQ": "2"}, {"CSP3_RL_W": "8"}, {"CSP3_RL_W": "2", "CSP3_RL_MARGIN": "-100000"}])
 def test_rowlane_program_other_geometries(env):
     """Other look-ahead depths / the natural column order (every chain reads late): knobs are read per process."""
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import numpy as np; "
             "import test_rowlane_program as t; from csparse3_b200 import synth; g = synth.GridCase(118); "
-            "n, Ap, Ai, Ax0 = g.base_jacobian(); Axb, bb = g.jacobian_batch(0, 3); t._check(n, Ap, Ai, Axb); print('ok')"
+            "n, Ap, Ai, Ax0 = g.base_jacobian(); Axb, bb = g.jacobian_batch(0, 3); t._check(n, Ap, Ai, Axb); "
+            "t.test_rowlane_program_small_matrices(1, 1e-3); print('ok')"
             ) % (ROOT, os.path.join(ROOT, "tests"))
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
