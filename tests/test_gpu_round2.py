@@ -198,3 +198,55 @@ def test_dmma_dense_update_and_supernodes():
     j = int(sn[np.argmax(w)])
     r0 = set(sym.Li[sym.Lp[j] + 1:sym.Lp[j + 1]]); r1 = set(sym.Li[sym.Lp[j + 1] + 1:sym.Lp[j + 2]])
     assert r0 - {j + 1} == r1
+
+
+@pytest.mark.parametrize("env", [{"CSP3_ROWLANE": "1", "CSP3_RL_W": "1"}, {"CSP3_ROWLANE": "1", "CSP3_RL_W": "2", "CSP3_RL_NQ": "1"},
+                                 {"CSP3_ROWLANE": "1", "CSP3_RL_W": "2", "CSP3_RL_NQ": "2"}, {"CSP3_ROWLANE": "1", "CSP3_RL_W": "4", "CSP3_RL_NQ": "2"},
+                                 {"CSP3_ROWLANE": "1", "CSP3_RL_W": "8"}, {"CSP3_ROWLANE": "1", "CSP3_RL_W": "4", "CSP3_RL_NQ": "2", "CSP3_RL_MARGIN": "-100000"},
+                                 {}])
+def test_rowlane_refactor_geometries(env):
+    """Row-lane refactor kernel (lu_rowlane.cu) with 1 / 2 / 4 / 8 warps per bundle, forced (CSP3_RL_W) and as the
+    automatic choice for small batches: factors and solutions bit-identical to the oracle on the 118-bus, 2,000-bus and
+    small irregular patterns, ragged batch sizes; a zero / non-finite pivot is reported with the oracle's code whichever
+    warp of the bundle eliminates that column.  The knobs are read once per process: child process."""
+    code = (
+        "import sys; sys.path.insert(0, %r); import numpy as np, torch, scipy.sparse as sp\n"
+        "from csparse3_b200 import synth; from csparse3_b200.lu import LuSymbolic; from oracle import oracle as orc\n"
+        "forced = %r\n"
+        "def check(n, Ap, Ai, Ax, b, sym):\n"
+        "    B = Ax.shape[0]\n"
+        "    name = sym.refactor_kernel_name(B)\n"
+        "    assert name == 'lu_refactor_rowlane_kernel' or (not forced and B > 444 * 8), name\n"
+        "    work = sym.workspace(B, 'cuda'); st = sym.refactor_ws(torch.as_tensor(Ax).cuda(), work)\n"
+        "    x = sym.solve_ws(work, torch.as_tensor(b).cuda()).cpu().numpy(); st = st.cpu().numpy()\n"
+        "    for k in range(B):\n"
+        "        try:\n"
+        "            Lx, Ux = orc.csc_lu_refactor(n, Ap, Ai, Ax[k], sym.q, sym.pinv, sym.Lp, sym.Li, sym.Up, sym.Ui); code = 0\n"
+        "        except Exception as e:\n"
+        "            code = -1\n"
+        "        if code == 0:\n"
+        "            assert st[k] == 0, (k, st[k])\n"
+        "            xo = orc.csc_lu_solve(n, sym.Lp, sym.Li, Lx, sym.Up, sym.Ui, Ux, sym.pinv, sym.q, b[k])\n"
+        "            assert np.array_equal(x[k], xo), k\n"
+        "        else:\n"
+        "            assert st[k] != 0, k\n"
+        "for nb, B in ((118, 37), (118, 520), (2000, 71)):\n"
+        "    g = synth.GridCase(nb); n, Ap, Ai, Ax0 = g.base_jacobian(); sym = LuSymbolic(n, Ap, Ai, Ax0)\n"
+        "    Ax, b = g.jacobian_batch(0, min(B, 71)); reps = -(-B // len(Ax)); Ax = np.tile(Ax, (reps, 1))[:B]; b = np.tile(b, (reps, 1))[:B]\n"
+        "    check(n, Ap, Ai, Ax, b, sym)\n"
+        "rng = np.random.default_rng(5)\n"
+        "for t in range(4):\n"
+        "    n = int(rng.integers(2, 200))\n"
+        "    A = sp.csc_matrix(sp.random(n, n, density=min(1.0, 3.0 / n + 0.03), random_state=int(rng.integers(1 << 30)), format='csc') + sp.diags(rng.uniform(0.5, 2.0, n)))\n"
+        "    Ap, Ai, Ax0 = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()\n"
+        "    sym = LuSymbolic(n, Ap, Ai, Ax0, order=1, tol=1e-3)\n"
+        "    Ax = Ax0[None, :] * rng.uniform(0.9, 1.1, (13, len(Ax0))); b = rng.standard_normal((13, n))\n"
+        "    check(n, Ap, Ai, Ax, b, sym)\n"
+        "# status codes: the pivot of the LAST column of system 1 is made zero, of a middle column of system 2 infinite\n"
+        "Ap = np.array([0, 1, 2, 5], dtype=np.int32); Ai = np.array([0, 1, 0, 1, 2], dtype=np.int32); Ax0 = np.array([2.0, 3.0, 1.0, 1.0, 4.0])\n"
+        "sym = LuSymbolic(3, Ap, Ai, Ax0, order=0, tol=1.0); Ax = np.tile(Ax0, (3, 1)); Ax[1, 4] = 0.0; Ax[2, 1] = np.inf\n"
+        "work = sym.workspace(3, 'cuda'); st = sym.refactor_ws(torch.as_tensor(Ax).cuda(), work).cpu().numpy()\n"
+        "assert st.tolist() == [0, 3, 2], st\n"
+        "print('ok')\n") % (ROOT, bool(env))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
