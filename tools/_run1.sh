@@ -1,8 +1,5 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_round2.py -x -q -m gpu -k "rowlane_refactor_geometries" 2>&1 | tail -3
-python bench.py --steps 20 --warmup 3 > gpurun_out/bench_r02c_n1_c3.json 2> gpurun_out/bench_r02c_n1_c3.err; tail -c 600 gpurun_out/bench_r02c_n1_c3.json
-python bench.py --batch 1250 --steps 20 --warmup 3 --no-secondary --no-cpu > gpurun_out/bench_r02c_n1_c3_b1250.json 2> gpurun_out/bench_r02c_n1_c3_b1250.err
-python bench.py --workload c4 --steps 5 --warmup 3 --no-secondary > gpurun_out/bench_r02c_n1_c4.json 2> gpurun_out/bench_r02c_n1_c4.err
-python bench.py --workload c4 --batch 1496 --steps 10 --warmup 3 --no-secondary --no-cpu > gpurun_out/bench_r02c_n1_c4_b1496.json 2> gpurun_out/bench_r02c_n1_c4_b1496.err
-python bench.py --workload c2 --steps 20 --warmup 3 --no-secondary > gpurun_out/bench_r02c_n1_c2.json 2> gpurun_out/bench_r02c_n1_c2.err
-python tools/latency.py > gpurun_out/latency_r02c.txt 2>&1
+ncu --set full --clock-control none --import-source on -k regex:rowlane -s 1 -c 1 -o gpurun_out/rl_w4_c3_3552 -f python tools/prof_lu.py --workload c3 --batch 3552 --iters 2 --check 0 > gpurun_out/ncu_rl_w4.log 2>&1
+ncu --set full --clock-control none -k regex:rowlane -s 1 -c 1 -o gpurun_out/rl_w8_c3_8 -f python tools/prof_lu.py --workload c3 --batch 8 --iters 2 --check 0 > gpurun_out/ncu_rl_w8.log 2>&1
+ncu --set full --clock-control none -k regex:rowlane -s 1 -c 1 -o gpurun_out/rl_w1_c4 -f python tools/prof_lu.py --workload c4 --batch 11926 --iters 2 --check 0 > gpurun_out/ncu_rl_w1_c4.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r02c_b1250.csv python bench.py --batch 1250 --steps 2 --warmup 1 --no-secondary --no-cpu > gpurun_out/ncu_launch_b1250.log 2>&1
