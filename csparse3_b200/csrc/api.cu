@@ -143,7 +143,11 @@ static void compile_wide(csp3_lu_symbolic &Sy)
     }
     if (t.wide == 0 || Sy.n == 0) return;
     const i32 width = (t.wide_S == 4 || t.wide_S == 16 || t.wide_S == 32) ? t.wide_S : 8;
-    const int ctas_per_sm[4] = {(10000 / width + kNumSMs - 1) / kNumSMs, 0, 0, 0};
+    // The wide kernel is the FULL-GPU kernel (smaller batches go to the row-lane kernel, lu_kernels.cu::rowlane_variant):
+    // its shared-memory budget per bundle is the one that keeps a full-GPU batch resident in one wave; larger budgets
+    // are tried below for patterns whose columns do not fit.
+    constexpr int kWideFullBatch = 10000;         // systems that should be resident in one wave: 9 bundles of 8 per SM
+    const int ctas_per_sm[4] = {(kWideFullBatch / width + kNumSMs - 1) / kNumSMs, 0, 0, 0};
     for (int i = 0; i < 3; ++i) {
         const int per_sm = std::max(1, ctas_per_sm[0] >> i);
         const size_t budget = t.wide_budget > 0 ? (size_t)t.wide_budget
