@@ -65,6 +65,7 @@ SIGNATURES = {
     "csp3_lu_solve_batched": [vp, i64, vp, vp, vp, vp, vp],
     "csp3_lu_workspace_bytes": [vp, i64],
     "csp3_lu_refactor_kernel_name": [vp, i64],
+    "csp3_lu_prepare": [vp, i64],
     "csp3_lu_refactor_solve_batched": [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp],
     "csp3_lu_refactor_ws": [vp, i64, vp, vp, vp, vp],
     "csp3_lu_solve_ws": [vp, i64, vp, vp, vp, vp],

@@ -810,6 +810,15 @@ const char *csp3_lu_refactor_kernel_name(const csp3_lu_symbolic *sym, int64_t ba
     return "lu_refactor_kernel";
 }
 
+int csp3_lu_prepare(const csp3_lu_symbolic *sym, int64_t batch)
+{
+    const DevSchedule *D = current_schedule(sym);
+    if (!D) return CSP3_ERR_ARG;
+    if (batch < 0) { set_error("lu_prepare: bad arguments"); return CSP3_ERR_ARG; }
+    (void)use_rowlane(*D, batch);              // compiles / uploads the row-lane program of this batch size when it is the choice
+    return 0;
+}
+
 int csp3_lu_refactor_batched(const csp3_lu_symbolic *sym, int64_t batch, const double *Ax, double *Lx,
                              double *Ux, int32_t *status, void *stream)
 {

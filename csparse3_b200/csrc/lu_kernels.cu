@@ -439,7 +439,8 @@ bool use_panel(const DevSchedule &D, i64 batch)
 //    when the batch fills the GPU (config 3: 6.6 ms for 1,250 bundles) but a bundle is one sequential walk (4.7 ms
 //    whatever the batch), and patterns with long columns leave 3 bundles per SM (config 4);
 //  * the row-lane kernel runs 1 / 2 / 4 / 8 warps per bundle on different columns (9 KB of shared memory per warp):
-//    8 warps up to 64 bundles (config 3: 1.8 ms), 4 warps up to one wave of 3 bundles per SM (2.3 - 2.8 ms), above
+//    8 warps (stages of one quad, 120 registers: two CTAs per SM) up to 2 bundles per SM (config 3: 1.66 ms for one
+//    bundle, 2.23 ms for 157), 4 warps up to one wave of 3 bundles per SM (2.4 - 2.8 ms), above
 //    that the wide kernel -- or, for the long-column patterns, one warp per bundle (config 4: 60.9 ms against 80.9 ms).
 //    (2 warps per bundle win by 10 % between 3 and 6 bundles per SM on an idle GPU, 4.8 against 5.3 ms at 625 bundles,
 //    but lose when two such launches share the GPU, as the chunks of csp3_nr_solve_host do: not selected automatically.)
@@ -451,7 +452,7 @@ int rowlane_variant(const DevSchedule &D, i64 batch)
     if (t.rl_warps > 0) return kRlVariants - 1;                       // CSP3_RL_W / CSP3_RL_NQ: forced geometry
     const i64 bundles = (batch + 7) / 8;
     const bool long_columns = D.wrf_smem > (size_t)40 * 1024;
-    if (bundles <= 64) return 3;
+    if (bundles <= (i64)2 * kNumSMs) return 3;
     if (bundles <= (i64)3 * kNumSMs) return 2;
     if (long_columns || t.rowlane > 0) return 0;
     return -1;

@@ -372,6 +372,9 @@ int launch_refactor_rowlane(const DevSchedule &D, i64 batch, const double *Ax, d
         case 1 * 8 + 3: return launch_T<1, 3>(a, grid, smem, st);
         case 2 * 8 + 1: return launch_T<2, 1>(a, grid, smem, st);
         case 2 * 8 + 2: return launch_T<2, 2>(a, grid, smem, st);
+        case 4 * 8 + 1: return launch_T<4, 1>(a, grid, smem, st);
+        case 8 * 8 + 1: return launch_T<8, 1>(a, grid, smem, st);
+        case 8 * 8 + 2: return launch_T<8, 2>(a, grid, smem, st);
         case 4 * 8 + 2: return launch_T<4, 2>(a, grid, smem, st);
         case 4 * 8 + 3: return launch_T<4, 3>(a, grid, smem, st);
         case 8 * 8 + 3: return launch_T<8, 3>(a, grid, smem, st);

@@ -196,6 +196,15 @@ class LuSymbolic:
             raise RuntimeError(_lib.last_error())
         return name.decode()
 
+    def prepare(self, batch, device=None):
+        """Upload the schedule and compile / upload the kernel program batches of this size use (otherwise done inside the
+        first refactor_ws call of that size, synchronously)."""
+        import torch
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(dev):
+            self._upload(dev.index if dev.index is not None else torch.cuda.current_device(), None)
+            check(_lib.lib().csp3_lu_prepare(self._h, int(batch)), "csp3_lu_prepare")
+
     def refactor_ws(self, Ax, work, status=None):
         """Refactor into the internal bundle-interleaved factor workspace (fast path, see workspace())."""
         import torch

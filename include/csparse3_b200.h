@@ -218,8 +218,16 @@ int csp3_lu_refactor_solve_batched(const csp3_lu_symbolic *sym, int64_t batch, c
 /* The two halves of the fused path, with the factors kept in `work` in the library's internal
  * bundle-interleaved layout (opaque to the caller; only csp3_lu_solve_ws with the same batch reads it).
  * This is the fast path: each factor entry of a bundle of systems is one contiguous run in HBM. */
+/* status[s]: 0, or k + 1 when column k of system s has a zero / non-finite pivot (the oracle's code), or -2 when the
+ * warps of a bundle lost their synchronisation (a defect, never seen: the kernel gives up instead of hanging).
+ * The kernel is chosen from `batch` (csp3_lu_refactor_kernel_name); the program of a geometry that has not been used
+ * on this device yet is compiled and uploaded inside the first call (synchronously: call csp3_lu_prepare first when
+ * the call must stay asynchronous, e.g. under stream capture). */
 int csp3_lu_refactor_ws(const csp3_lu_symbolic *sym, int64_t batch, const double *Ax, void *work,
                         int32_t *status, void *stream);
+/* Makes everything csp3_lu_refactor_ws / csp3_lu_solve_ws need for batches of `batch` systems resident on the current
+ * device (compiles the kernel program of that batch size on first use).  Idempotent. */
+int csp3_lu_prepare(const csp3_lu_symbolic *sym, int64_t batch);
 int csp3_lu_solve_ws(const csp3_lu_symbolic *sym, int64_t batch, void *work, const double *b, double *x,
                      void *stream);
 
