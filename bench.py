@@ -465,6 +465,29 @@ def main():
     same = bool(np.array_equal(x_np, x_d.cpu().numpy()))
     assert same and (st_np == 0).all(), "host-buffer path and device path disagree"
 
+    # ---- small batches on this GPU (one system; 1/8 of the workload = one rank's shard at N = 8): the refactorisation picks
+    # ---- its kernel from the batch (several warps per bundle for these), device resident, results compared with the big run
+    small = []
+    if world == 1:
+        for nb in sorted({min(B, 1), min(B, 8), max(1, -(-B // 8))}):
+            As, bs = Ax_d[:nb].contiguous(), b_d[:nb].contiguous()
+            ws_ = sym.workspace(nb, dev); xs = torch.empty((nb, n), dtype=torch.float64, device=dev)
+            ss = torch.empty(nb, dtype=torch.int32, device=dev)
+            for _ in range(3):
+                sym.refactor_ws(As, ws_, ss); sym.solve_ws(ws_, bs, xs)
+            ev3 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            reps = 10
+            torch.cuda.synchronize()
+            rf_t = sv_t = 0.0
+            for _ in range(reps):
+                ev3[0].record(); sym.refactor_ws(As, ws_, ss); ev3[1].record(); sym.solve_ws(ws_, bs, xs); ev3[2].record()
+                torch.cuda.synchronize()
+                rf_t += ev3[0].elapsed_time(ev3[1]); sv_t += ev3[1].elapsed_time(ev3[2])
+            small.append({"systems": nb, "refactor_ms": rf_t / reps, "solve_ms": sv_t / reps, "systems_per_s": nb / ((rf_t + sv_t) / reps * 1e-3),
+                          "refactor_kernel": sym.refactor_kernel_name(nb),
+                          "bit_identical_to_full_batch": bool(torch.equal(xs, x_d[:nb])) and int(ss.abs().max().item()) == 0})
+            del As, bs, ws_, xs, ss
+
     # ---- weak-scaling point in the same run (the workload's batch per GPU), for the scaling curve's other reading -------
     weak = None
     if world > 1 and args.scaling == "strong":
@@ -515,6 +538,7 @@ def main():
                "refactor_flops_per_system": sym.flops, "levels": sym.nlev_refactor,
                "l2": "inputs larger than L2 (%.2f GB of values per step, nothing reused across steps)" % (step_bytes / 1e9),
                "parallelism": "batch-sharded x%d, no collective in refactor/solve%s" % (world, "; gather of x to rank 0 inside the timed step" if world > 1 else ""),
+               "small_batches": small,
                "kernel_ms": {rf_name: rf_ms, (sv_name + " x2 + rhs_to_bundles_kernel + bundles_to_x_kernel") if wide else sv_name: sv_ms},
                "result_gather_ms": ga_ms if world > 1 else None,
                "bundle": ("%d systems per warp, 2 per lane" % sym.wide_width) if wide else "v3 kernels",
