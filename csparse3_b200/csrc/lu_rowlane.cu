@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(32 * W, (W == 2 && NQ == 1) ? 10 : 1) lu_refac
     };
     // have the other warps finished the columns the stage at ring address sb reads?  (8 x 16-bit counters)
     auto sources_final = [&](unsigned sb) -> bool {
+        if (!(lds_u32(sb) & kRlFlagCross)) return true;                // the stage reads no column of another warp
         const uint4 req = lds_u4(sb + 32);
         uint4 done;
         asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(done.x), "=r"(done.y), "=r"(done.z), "=r"(done.w) : "r"(flags_s) : "memory");
@@ -258,7 +259,10 @@ __global__ void __launch_bounds__(32 * W, (W == 2 && NQ == 1) ? 10 : 1) lu_refac
                 sink ^= (unsigned)__double2hiint(C[0].x);
             }
             haveQ = sources_final(sb1);
-            if (haveQ) { __threadfence_block(); request_operands(sb1, Q); }
+            if (haveQ) {
+                if (lds_u32(sb1) & kRlFlagCross) __threadfence_block();       // other warps' L stores before our loads
+                request_operands(sb1, Q);
+            }
         } else {
             request_operands(sb1, Q);
         }

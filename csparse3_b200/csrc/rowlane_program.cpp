@@ -285,6 +285,8 @@ bool compile_rowlane_refactor(i64 n64, const i32 *Ap, const std::vector<i32> &q,
         for (i32 p = uptr[k]; p < uptr[(size_t)k + 1]; ++p)
             if (--ndeps[users[(size_t)p]] == 0) ready.insert(users[(size_t)p]);
     }
+    for (i32 w = 0; w < warps; ++w)
+        if (warps > 1 && st[(size_t)w].ncols > 65535) { *why = "row-lane program: more than 65535 columns on one warp (16-bit progress counters)"; return false; }
     Quad endq;
     endq.kind(kRlEnd);
     P.quads = 0;
@@ -297,7 +299,10 @@ bool compile_rowlane_refactor(i64 n64, const i32 *Ap, const std::vector<i32> &q,
         while (T.quads.size() < padded) T.quads.push_back(endq);
         // cross-warp requirements of a stage ride in the spare header words of its first quad (8 x 16 bits)
         for (size_t sg = 0; sg < T.req.size(); ++sg)
-            for (int v = 0; v < kRlMaxWarps; ++v) T.quads[sg * (size_t)NQ].w[8 + v / 2] |= (uint32_t)T.req[sg][(size_t)v] << (16 * (v & 1));
+            for (int v = 0; v < kRlMaxWarps; ++v) {
+                T.quads[sg * (size_t)NQ].w[8 + v / 2] |= (uint32_t)T.req[sg][(size_t)v] << (16 * (v & 1));
+                if (T.req[sg][(size_t)v]) T.quads[sg * (size_t)NQ].w[0] |= kRlFlagCross;
+            }
         P.stream_off[w] = (i64)P.words.size() / kRlQuadWords;
         const size_t base = P.words.size();
         P.words.resize(base + T.quads.size() * kRlQuadWords);

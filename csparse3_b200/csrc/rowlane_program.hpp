@@ -32,6 +32,7 @@
 //
 // Quad = 76 words:
 //   h0.x    bits 0-2 kind; bits 8-11 UPDATE: NEW[r], FIN: bit 8 has L, bit 9 has U, bit 10 has A; bit 12 P;
+//           bit 13 (first quad of a stage) the stage reads columns of other warps (h2);
 //           bits 16-18 count (STOREL4 / STOREU4 / LOAD4); bits 24-31 FIN / STOREL4 / STOREU4 / LOAD4: role of record r
 //           in bits 24 + 2 r (0 none, 1 L store, 2 U store, 3 A load), what the kernel's shared loop executes
 //   h0.y    mslot[0] * 64 | mslot[1] * 64 << 16        h0.z   mslot[2] * 64 | mslot[3] * 64 << 16
@@ -52,6 +53,7 @@ namespace csp3 {
 
 enum : int { kRlNop = 0, kRlLoad4 = 1, kRlUpdate = 2, kRlStoreU4 = 3, kRlStoreL4 = 4, kRlUpdLate = 5, kRlFin = 6, kRlEnd = 7 };
 enum : unsigned { kRlRoleL = 1, kRlRoleU = 2, kRlRoleA = 3 };
+enum : unsigned { kRlFlagCross = 1u << 13 };      // first quad of a stage: the stage has cross-warp requirements (h2 != 0)
 enum : unsigned { kRlFlagP = 1u << 12, kRlHasL = 1u << 8, kRlHasU = 1u << 9, kRlHasA = 1u << 10 };
 constexpr int kRlOps = 8;              // operations per record (lane groups)
 constexpr int kRlMaxSlots = 1024;      // accumulator slots (slot * 64 is a 16-bit byte offset)

@@ -87,7 +87,7 @@ def run_refactor(sym, Axb, seed=0):
     def sources_final(x, s):
         qd = x.first + s * SQ
         r = req16[qd]
-        assert r[x.w] == 0
+        assert r[x.w] == 0 and bool(r.any()) == bool(h0[qd, 0] & (1 << 13))
         return bool((done >= r).all())
 
     def request_stage(x, s):
