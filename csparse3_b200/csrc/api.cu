@@ -202,10 +202,10 @@ int ensure_rowlane_variant(const DevSchedule &D, int variant)
 {
     if (variant < 0 || variant >= kRlVariants || !D.owner) return -1;
     DevSchedule::RlVariant &R = D.rl[variant];
-    if (R.tried) return R.ok ? 0 : -1;
+    if (R.tried.load(std::memory_order_acquire)) return R.ok ? 0 : -1;
     csp3_lu_symbolic &Sy = *static_cast<csp3_lu_symbolic *>(D.owner);
     std::lock_guard<std::mutex> lock(Sy.rl_mu);
-    if (R.tried) return R.ok ? 0 : -1;
+    if (R.tried.load(std::memory_order_relaxed)) return R.ok ? 0 : -1;
     const RowlaneProgram *P = rowlane_program(Sy, variant);
     if (P && P->smem_bytes <= (size_t)200 * 1024) {
         uint8_t *dev = nullptr;
@@ -219,7 +219,7 @@ int ensure_rowlane_variant(const DevSchedule &D, int variant)
             cudaGetLastError();
         }
     }
-    R.tried = true;
+    R.tried.store(true, std::memory_order_release);
     return R.ok ? 0 : -1;
 }
 }  // namespace csp3

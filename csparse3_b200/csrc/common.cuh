@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -57,7 +58,8 @@ struct DevSchedule {
     // row-lane refactor program (lu_rowlane.cu), bundles of 8 systems
     // (one program per geometry: warps per bundle x quads per stage, compiled and uploaded on first use)
     struct RlVariant {
-        bool ok = false, tried = false;
+        bool ok = false;
+        std::atomic<bool> tried{false};    // set (release) after ok / prog / ... are final: readers that see it need no lock
         uint8_t *prog = nullptr;           // own device allocation
         i32 quads = 0, nslots = 0, warps = 1, stage_quads = 3, stream_off[8] = {};
         size_t smem = 0;
