@@ -282,6 +282,31 @@ __global__ void __launch_bounds__(32 * W, (W == 2 && NQ == 1) ? 10 : 1) lu_refac
                 update_op(lq.w, accb, C[qd * NR + 3], m);
                 continue;
             }
+            if (NQ <= 2 && kind == (unsigned)kRlFin) {
+                // (stages of 1 - 2 quads: the several-warps geometries; with 3 quads per stage the six copies of this
+                // path cost more in the instruction cache than they save: config 4, one warp per bundle, 61 -> 79 ms)
+                // column boundary, once per column and on the critical path of the warps that wait for this column: all
+                // shared-memory loads first, the U entries / clearing / the next column's A values while the reciprocal
+                // of the pivot is refined, the divisions last
+                const uint4 bs = lds_u4(qa + 16);
+                const bool vL = (hq.x & kRlHasL) && f_valid(lq.x), vU = (hq.x & kRlHasU) && f_valid(lq.y), vA = (hq.x & kRlHasA) && f_valid(lq.z);
+                const unsigned tL = accb + f_slot64(lq.x), tU = accb + f_slot64(lq.y);
+                double2 xp = piv;
+                if (hq.x & kRlFlagP) xp = lds_d2(accb + (hq.y & 0xffffu));
+                const double2 xL = lds_d2(tL), xU = lds_d2(tU);          // (an empty word carries a readable slot)
+                if (vU) { sts_d2(tU, zero2); stg_cs_d2(Ub + (size_t)(bs.y + f_off64(lq.y)), xU); }
+                if (vL) sts_d2(tL, zero2);
+                if (vA) sts_d2(accb + f_slot64(lq.z), C[qd * NR + 2]);    // after the clearing: the next column reuses the slots
+                if (hq.x & kRlFlagP) {
+                    piv = xp;
+                    rcp = make_double2(rcp_refined(piv.x), rcp_refined(piv.y));
+                    if (!(fabs(piv.x) > 0.0 && isfinite(piv.x))) fail0 = min(fail0, (int)hq.w);
+                    if (!(fabs(piv.y) > 0.0 && isfinite(piv.y))) fail1 = min(fail1, (int)hq.w);
+                }
+                if (vL) stg_d2(Lb + (size_t)(bs.x + f_off64(lq.x)), make_double2(div_shared(xL.x, piv.x, rcp.x), div_shared(xL.y, piv.y, rcp.y)));
+                ++cols_done;
+                continue;
+            }
             if (kind == (unsigned)kRlUpdLate) {
                 // rare: a source column of this warp was finalised less than two stages ago, read the operands now
                 const uint4 aw = lds_u4(qa + aw_off);
@@ -299,7 +324,8 @@ __global__ void __launch_bounds__(32 * W, (W == 2 && NQ == 1) ? 10 : 1) lu_refac
                     update_op(word_of(lq, r), accb, l[r], m);
                 }
             } else if (kind != (unsigned)kRlEnd) {
-                // FIN / STOREL4 / STOREU4 / LOAD4: one shared loop over the records, role by role (once per column)
+                // STOREL4 / STOREU4 / LOAD4 (columns with more than 8 entries of a role; FIN with 3 quads per stage): one
+                // shared loop over the records
                 if (hq.x & kRlFlagP) pivot_prologue(hq);
                 unsigned roles = hq.x >> 24;
 #pragma unroll 1
@@ -374,6 +400,8 @@ int launch_refactor_rowlane(const DevSchedule &D, i64 batch, const double *Ax, d
     const size_t smem = R.smem;
     switch (R.warps * 8 + R.stage_quads) {
         case 1 * 8 + 3: return launch_T<1, 3>(a, grid, smem, st);
+        case 1 * 8 + 2: return launch_T<1, 2>(a, grid, smem, st);
+        case 1 * 8 + 1: return launch_T<1, 1>(a, grid, smem, st);
         case 2 * 8 + 1: return launch_T<2, 1>(a, grid, smem, st);
         case 2 * 8 + 2: return launch_T<2, 2>(a, grid, smem, st);
         case 4 * 8 + 1: return launch_T<4, 1>(a, grid, smem, st);
