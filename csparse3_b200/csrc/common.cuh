@@ -26,7 +26,7 @@ const char *get_error();
 constexpr int kNumSMs = 148;   // B200
 // row-lane refactor program geometries (warps per bundle, quads per stage); the last one is the CSP3_RL_W / CSP3_RL_NQ override
 constexpr int kRlVariants = 5;
-constexpr int kRlGeometry[kRlVariants][2] = {{1, 1}, {2, 2}, {4, 2}, {8, 1}, {0, 0}};
+constexpr int kRlGeometry[kRlVariants][2] = {{1, 3}, {2, 2}, {4, 2}, {8, 1}, {0, 0}};
 
 // ---- device copy of the LU schedule (one per device) ------------------------------------------------------
 struct DevSchedule {
