@@ -122,7 +122,10 @@ __device__ __forceinline__ void load_multiplier(double2 &m, unsigned addr, unsig
 // requests the operands of a stage whose sources belong to them: ahead of time when they are already final, otherwise
 // when the stage is reached (everything before it has been executed and published by then: no deadlock).
 template <int W, int NQ>
-__global__ void __launch_bounds__(32 * W, (W == 2 && NQ == 1) ? 10 : 1) lu_refactor_rowlane_kernel(const RowlaneArgs a)
+// (resident CTAs per SM the selection rule of lu_kernels.cu::rowlane_variant counts on: 8 warps x one-quad stages: 2,
+// 4 warps x two-quad stages: 3; 2 warps x one-quad stages: 10, every bundle of a 10,000-system batch resident)
+__global__ void __launch_bounds__(32 * W, (W == 2 && NQ == 1) ? 10 : (W == 8 && NQ == 1) ? 2 : (W == 4 && NQ == 2) ? 3 : 1)
+    lu_refactor_rowlane_kernel(const RowlaneArgs a)
 {
     constexpr int S = 8, NR = kRlQuadRecords, SR = NQ * NR;
     constexpr unsigned QUAD_BYTES = kRlQuadWords * 4, STAGE_BYTES = NQ * QUAD_BYTES, RING_BYTES = kRlRingStages * STAGE_BYTES;
