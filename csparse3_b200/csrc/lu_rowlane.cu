@@ -40,18 +40,6 @@ __device__ __forceinline__ double ldg_nc_f64(const void *p)
     asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
-__device__ __forceinline__ uint4 ldg_nc_u4(const void *p)
-{
-    uint4 v;
-    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ unsigned ldg_nc_u32(const void *p)
-{
-    unsigned v;
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
 __device__ __forceinline__ void stg_d2(void *p, double2 v) { asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory"); }
 __device__ __forceinline__ void stg_cs_d2(void *p, double2 v) { asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory"); }
 
