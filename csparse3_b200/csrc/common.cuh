@@ -90,7 +90,7 @@ int launch_growth(const DevSchedule &D, i64 batch, const double *Lw, double *gro
 int launch_refactor_panel(const DevSchedule &D, i64 batch, const double *Ax, double *Lw, double *Uw, i32 *status,
                           double *growth, cudaStream_t st);
 bool use_rowlane(const DevSchedule &D, i64 batch);
-int rowlane_variant(const DevSchedule &D, i64 batch);      // index into DevSchedule::rl, or -1: not the row-lane kernel
+int rowlane_variant(const DevSchedule &D, i64 batch);      // index into DevSchedule::rl (compiled and uploaded), or -1: not the row-lane kernel
 int ensure_rowlane_variant(const DevSchedule &D, int variant);   // api.cu: compiles / uploads on first use; 0 when available
 int launch_refactor_rowlane(const DevSchedule &D, i64 batch, const double *Ax, double *Lw, double *Uw, i32 *status, cudaStream_t st);
 int launch_solve_wide(const DevSchedule &D, i64 batch, const double *Lw, const double *Uw, const double *b, double *x,

@@ -449,20 +449,17 @@ int rowlane_variant(const DevSchedule &D, i64 batch)
     const Tuning &t = tuning();
     if (!D.rl_enabled || t.rowlane == 0 || t.ws_S != 0) return -1;
     if (t.rowlane < 0 && (t.tmem != 0 || t.panel != 0)) return -1;      // an experimental kernel was asked for explicitly
-    if (t.rl_warps > 0) return kRlVariants - 1;                       // CSP3_RL_W / CSP3_RL_NQ: forced geometry
+    if (t.rl_warps > 0) return ensure_rowlane_variant(D, kRlVariants - 1) == 0 ? kRlVariants - 1 : -1;   // CSP3_RL_W / CSP3_RL_NQ: forced geometry
     const i64 bundles = (batch + 7) / 8;
     const bool long_columns = D.wrf_smem > (size_t)40 * 1024;
-    if (bundles <= (i64)2 * kNumSMs) return 3;
-    if (bundles <= (i64)3 * kNumSMs) return 2;
-    if (long_columns || t.rowlane > 0) return 0;
+    // a geometry may be unavailable for a pattern (8 accumulators of a very long column exceed shared memory): next one
+    if (bundles <= (i64)2 * kNumSMs && ensure_rowlane_variant(D, 3) == 0) return 3;
+    if (bundles <= (i64)3 * kNumSMs && ensure_rowlane_variant(D, 2) == 0) return 2;
+    if ((long_columns || t.rowlane > 0) && ensure_rowlane_variant(D, 0) == 0) return 0;
     return -1;
 }
 
-bool use_rowlane(const DevSchedule &D, i64 batch)
-{
-    const int v = rowlane_variant(D, batch);
-    return v >= 0 && ensure_rowlane_variant(D, v) == 0;
-}
+bool use_rowlane(const DevSchedule &D, i64 batch) { return rowlane_variant(D, batch) >= 0; }
 // (use_tmem: lu_wide.cu.  With the panel kernel selected the factors stay in 8-system bundles.)
 
 int workspace_bundle_width(const DevSchedule &D, i64 batch)

@@ -380,7 +380,7 @@ int launch_refactor_rowlane(const DevSchedule &D, i64 batch, const double *Ax, d
 {
     if (batch <= 0) return 0;
     const int v = rowlane_variant(D, batch);
-    if (v < 0 || ensure_rowlane_variant(D, v) != 0) { set_error("row-lane refactor program not available for this pattern"); return -1; }
+    if (v < 0) { set_error("row-lane refactor program not available for this pattern"); return -1; }
     const DevSchedule::RlVariant &R = D.rl[v];
     RowlaneArgs a;
     a.prog = R.prog;
