@@ -85,3 +85,24 @@ def test_rowlane_program_other_geometries(env):
             ) % (ROOT, os.path.join(ROOT, "tests"))
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_rowlane_program_laplacians_many_warps():
+    """Patterns with wide elimination trees and long columns (2-D / 3-D Laplacians): several warps per bundle, different
+    interleavings of the warps, overflow quads (more than 8 entries of a role per column)."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import numpy as np; "
+            "import rowlane_interp as ri; from csparse3_b200 import synth; from csparse3_b200.lu import LuSymbolic; "
+            "from oracle import oracle as orc\n"
+            "for n, Ap, Ai, Ax in (synth.laplacian_2d(24), synth.laplacian_3d(7)):\n"
+            "    rng = np.random.default_rng(3); Axb = Ax[None, :] * rng.uniform(0.9, 1.1, (2, len(Ax)))\n"
+            "    sym = LuSymbolic(n, Ap, Ai, Axb[0])\n"
+            "    for seed in (0, 1):\n"
+            "        Lx, Ux, fail, stats = ri.run_refactor(sym, Axb, seed=seed)\n"
+            "        for k in range(2):\n"
+            "            L, U = orc.csc_lu_refactor(n, Ap, Ai, Axb[k], sym.q, sym.pinv, sym.Lp, sym.Li, sym.Up, sym.Ui)\n"
+            "            assert np.array_equal(Lx[k], L) and np.array_equal(Ux[k], U)\n"
+            "        assert (fail == 0).all() and stats['ops'] * 2 == sym.flops\n"
+            "print('ok')") % (ROOT, os.path.join(ROOT, "tests"))
+    for env in ({"CSP3_RL_W": "8", "CSP3_RL_NQ": "1"}, {"CSP3_RL_W": "4", "CSP3_RL_NQ": "2"}):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True)
+        assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
