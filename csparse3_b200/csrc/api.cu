@@ -12,6 +12,7 @@
 #include "csc_kernels.cuh"
 #include "panel_program.hpp"
 #include "rowlane_program.hpp"
+#include "rowsweep_program.hpp"
 
 namespace csp3 {
 
@@ -40,6 +41,7 @@ Tuning &tuning()
         if (getenv("CSP3_PANEL")) v.panel = env("CSP3_PANEL");
         if (getenv("CSP3_TMEM")) v.tmem = env("CSP3_TMEM");
         if (getenv("CSP3_ROWLANE")) v.rowlane = env("CSP3_ROWLANE");
+        if (getenv("CSP3_ROWSWEEP")) v.rowsweep = env("CSP3_ROWSWEEP");
         v.rl_warps = env("CSP3_RL_W"); v.rl_nq = env("CSP3_RL_NQ");
         v.panel_fma = env("CSP3_PANEL_FMA");
         v.panel_budget = env("CSP3_PANEL_BUDGET");
@@ -105,6 +107,8 @@ struct csp3_lu_symbolic {
     PanelProgram PP;                   // panel refactor program (lu_panel.cu); ok == false: the wide / v3 kernels are used
     RowlaneProgram RL[kRlVariants];    // row-lane refactor programs (lu_rowlane.cu), one per geometry, compiled on first use
     bool RLtried[kRlVariants] = {};
+    RowSweepProgram RSf, RSb;          // row-sweep programs (forward / backward), compiled on first use
+    bool RStried = false;
     std::mutex rl_mu;                  // guards RL / RLtried and the per-device variants (taken inside calls that may hold `mu`)
     std::vector<i32> qinv;             // x[c] = x_pivot_order[qinv[c]]
     DevSchedule dev[kMaxDevices];
@@ -216,6 +220,43 @@ int ensure_rowlane_variant(const DevSchedule &D, int variant)
             R.ok = true;
         } else {
             if (dev) cudaFree(dev);
+            cudaGetLastError();
+        }
+    }
+    R.tried.store(true, std::memory_order_release);
+    return R.ok ? 0 : -1;
+}
+int ensure_rowsweep(const DevSchedule &D)
+{
+    if (!D.owner) return -1;
+    DevSchedule::RsPrograms &R = D.rs;
+    if (R.tried.load(std::memory_order_acquire)) return R.ok ? 0 : -1;
+    csp3_lu_symbolic &Sy = *static_cast<csp3_lu_symbolic *>(D.owner);
+    std::lock_guard<std::mutex> lock(Sy.rl_mu);
+    if (R.tried.load(std::memory_order_relaxed)) return R.ok ? 0 : -1;
+    if (!Sy.RStried) {
+        Sy.RStried = true;
+        const char *why = "";
+        if (!compile_row_sweep(Sy.F, Sy.S, true, Sy.RSf, &why) || !compile_row_sweep(Sy.F, Sy.S, false, Sy.RSb, &why)) {
+            if (getenv("CSP3_DEBUG")) fprintf(stderr, "csp3: row sweeps unavailable: %s\n", why);
+            Sy.RSf = RowSweepProgram(); Sy.RSb = RowSweepProgram();
+        } else if (getenv("CSP3_DEBUG")) {
+            fprintf(stderr, "csp3: row sweeps: forward %d levels, %d panels, %lld chunks for %lld terms; backward %d levels, %d panels, %lld chunks for %lld terms\n",
+                    Sy.RSf.levels, Sy.RSf.panels, (long long)Sy.RSf.chunks, (long long)Sy.RSf.terms, Sy.RSb.levels, Sy.RSb.panels, (long long)Sy.RSb.chunks, (long long)Sy.RSb.terms);
+        }
+    }
+    if (Sy.RSf.ok && Sy.RSb.ok) {
+        uint32_t *df = nullptr, *db = nullptr;
+        const size_t bf = Sy.RSf.words.size() * 4, bb = Sy.RSb.words.size() * 4;
+        if (cudaMalloc((void **)&df, bf) == cudaSuccess && cudaMalloc((void **)&db, bb) == cudaSuccess &&
+            cudaMemcpy(df, Sy.RSf.words.data(), bf, cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMemcpy(db, Sy.RSb.words.data(), bb, cudaMemcpyHostToDevice) == cudaSuccess) {
+            R.prog_f = df; R.prog_b = db; R.levels_f = Sy.RSf.levels; R.levels_b = Sy.RSb.levels;
+            for (int w = 0; w < kRsWarps; ++w) { R.stream_off_f[w] = (i32)Sy.RSf.stream_off[w]; R.stream_off_b[w] = (i32)Sy.RSb.stream_off[w]; }
+            R.ok = true;
+        } else {
+            if (df) cudaFree(df);
+            if (db) cudaFree(db);
             cudaGetLastError();
         }
     }
@@ -640,6 +681,24 @@ int64_t csp3_lu_get_program(const csp3_lu_symbolic *sym, int which, uint8_t *buf
         case 6: P = sym->PP.ok ? &sym->PP.prog : nullptr; break;
         default: break;
     }
+    if (which == 9 || which == 10) {                     // row-sweep programs (rowsweep_program.hpp): 9 forward, 10 backward
+        csp3_lu_symbolic &Sy = *const_cast<csp3_lu_symbolic *>(sym);
+        std::lock_guard<std::mutex> lock(Sy.rl_mu);
+        if (!Sy.RStried) {
+            Sy.RStried = true;
+            const char *why = "";
+            if (!compile_row_sweep(Sy.F, Sy.S, true, Sy.RSf, &why) || !compile_row_sweep(Sy.F, Sy.S, false, Sy.RSb, &why)) { Sy.RSf = RowSweepProgram(); Sy.RSb = RowSweepProgram(); }
+        }
+        const RowSweepProgram &RS = which == 9 ? Sy.RSf : Sy.RSb;
+        if (!RS.ok) { set_error("lu_get_program: program %d not available", which); return CSP3_ERR_ARG; }
+        if (geometry) {
+            std::memset(geometry, 0, 8 * sizeof(int64_t));
+            geometry[0] = RS.levels; geometry[1] = RS.warps; geometry[2] = RS.panels; geometry[3] = RS.chunks; geometry[4] = RS.terms;
+            for (int w = 0; w < 3; ++w) geometry[5 + w] = RS.stream_off[w + 1];      // (all offsets follow from the END panels as well)
+        }
+        if (buf && capacity >= (int64_t)(RS.words.size() * 4)) std::memcpy(buf, RS.words.data(), RS.words.size() * 4);
+        return (int64_t)(RS.words.size() * 4);
+    }
     if (which == 7) {                                    // row-lane program: 44 words per quad (rowlane_program.hpp)
         // the geometry CSP3_RL_W / CSP3_RL_NQ ask for, otherwise one warp per bundle (compiled here when not yet cached)
         csp3_lu_symbolic &Sy = *const_cast<csp3_lu_symbolic *>(sym);
@@ -698,6 +757,8 @@ int csp3_lu_destroy(csp3_lu_symbolic *sym)
         if (have) cudaSetDevice(d);
         if (sym->dev[d].arena) cudaFree(sym->dev[d].arena);
         for (auto &R : sym->dev[d].rl) if (R.prog) cudaFree(R.prog);
+        if (sym->dev[d].rs.prog_f) cudaFree(sym->dev[d].rs.prog_f);
+        if (sym->dev[d].rs.prog_b) cudaFree(sym->dev[d].rs.prog_b);
         if (sym->stage[d].ready) free_stage(sym->stage[d]);
     }
     if (have) cudaSetDevice(cur);

@@ -65,6 +65,14 @@ struct DevSchedule {
         size_t smem = 0;
     };
     mutable RlVariant rl[kRlVariants];
+    // row-sweep programs (lu_sweep_rows_kernel in lu_wide.cu): the sweeps of a small batch on 8 warps per bundle
+    struct RsPrograms {
+        bool ok = false;
+        std::atomic<bool> tried{false};
+        uint32_t *prog_f = nullptr, *prog_b = nullptr;     // own device allocations
+        i32 levels_f = 0, levels_b = 0, stream_off_f[8] = {}, stream_off_b[8] = {};
+    };
+    mutable RsPrograms rs;
     bool rl_enabled = false;               // the sweeps this kernel's factor layout needs are available
     void *owner = nullptr;                 // csp3_lu_symbolic the schedule belongs to (lazy compilation of the variants)
     int devid = 0;
@@ -93,6 +101,9 @@ bool use_rowlane(const DevSchedule &D, i64 batch);
 int rowlane_variant(const DevSchedule &D, i64 batch);      // index into DevSchedule::rl (compiled and uploaded), or -1: not the row-lane kernel
 int ensure_rowlane_variant(const DevSchedule &D, int variant);   // api.cu: compiles / uploads on first use; 0 when available
 int launch_refactor_rowlane(const DevSchedule &D, i64 batch, const double *Ax, double *Lw, double *Uw, i32 *status, cudaStream_t st);
+bool use_rowsweep(const DevSchedule &D, i64 batch);
+int ensure_rowsweep(const DevSchedule &D);                   // api.cu: compiles / uploads on first use; 0 when available
+int launch_solve_rows(const DevSchedule &D, i64 batch, const double *Lw, const double *Uw, const double *b, double *x, double *z1, cudaStream_t st);
 int launch_solve_wide(const DevSchedule &D, i64 batch, const double *Lw, const double *Uw, const double *b, double *x,
                       double *z1, double *z2, cudaStream_t st);
 
@@ -103,6 +114,7 @@ struct Tuning {
     int rf_S = 0, sv_S = 0, ws_S = 0, rf_win = 0, sv_stage = 0;
     int tmem = 0;                          // CSP3_TMEM=1: experimental refactor kernel with the accumulator in tensor memory (lu_refactor_tmem_kernel)
     int panel = 0, panel_fma = 0, panel_budget = 0;          // CSP3_PANEL=1 selects the experimental panel refactor kernel (lu_panel.cu), CSP3_PANEL_FMA (fused multiply-add, not bit-exact)
+    int rowsweep = 0;                      // CSP3_ROWSWEEP=1: row-oriented sweeps on 8 warps per bundle for small batches (lu_sweep_rows_kernel)
     int rowlane = -1, rl_warps = 0, rl_nq = 0;        // row-lane refactor kernel (lu_rowlane.cu): -1 automatic (patterns whose wide program leaves < 5 bundles per SM), CSP3_ROWLANE=0 / 1 never / always; CSP3_RL_W warps per bundle (1, 2, 4, 8), CSP3_RL_NQ quads per stage
     int wide = 1, wide_solve = 1, wide_S = 0, wide_R = 0, wide_ring = 0, wide_stage = 0, wide_budget = 0;   // CSP3_WIDE (0 disables), CSP3_WIDE_S/_R/_F/_BUDGET
 };

@@ -460,6 +460,15 @@ int rowlane_variant(const DevSchedule &D, i64 batch)
 }
 
 bool use_rowlane(const DevSchedule &D, i64 batch) { return rowlane_variant(D, batch) >= 0; }
+
+// The sweeps of a small batch: row by row on 8 warps per bundle, in the regime where the refactorisation runs 8 warps per
+// bundle too (up to 2 bundles per SM); otherwise the wide sweeps (one warp per bundle).
+bool use_rowsweep(const DevSchedule &D, i64 batch)
+{
+    if (tuning().rowsweep == 0 || !D.rl_enabled || tuning().ws_S != 0 || tuning().tmem != 0 || tuning().panel != 0) return false;
+    if ((batch + 7) / 8 > (i64)2 * kNumSMs && tuning().rowsweep < 2) return false;
+    return ensure_rowsweep(D) == 0;
+}
 // (use_tmem: lu_wide.cu.  With the panel kernel selected the factors stay in 8-system bundles.)
 
 int workspace_bundle_width(const DevSchedule &D, i64 batch)
@@ -559,6 +568,7 @@ int launch_solve(const DevSchedule &D, i64 batch, const double *Lx, const double
                  double *x, double *z, bool interleaved, cudaStream_t st)
 {
     if (batch <= 0) return 0;
+    if (interleaved && use_rowsweep(D, batch)) return launch_solve_rows(D, batch, Lx, Ux, b, x, z, st);
     if (interleaved && use_wide(D, batch) && D.wide_solve_ok && tuning().wide_solve != 0) {
         const i64 padded = (batch + 31) / 32 * 32;
         return launch_solve_wide(D, batch, Lx, Ux, b, x, z, z + padded * D.n, st);

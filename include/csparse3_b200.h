@@ -189,7 +189,8 @@ int64_t csp3_lu_get_program(const csp3_lu_symbolic *sym, int which, uint8_t *buf
                             int64_t geometry[8]);
 /* (which = 6: panel refactor, 7: row-lane refactor -- 76 words per quad, csparse3_b200/csrc/rowlane_program.hpp;
  * geometry [0] update quads, [1] quads per stage, [2] accumulator slots, [3] late quads, [4] update operations,
- * [5] quads, [6] smem bytes, [7] update records.) */
+ * [5] quads, [6] smem bytes, [7] update records.  which = 9 / 10: forward / backward row-sweep program,
+ * csparse3_b200/csrc/rowsweep_program.hpp; geometry [0] levels, [1] warps, [2] panels, [3] chunks, [4] terms.) */
 /* Name of the refactorisation kernel the workspace path (csp3_lu_refactor_ws) runs for `batch` systems on the
  * current device (the symbolic object must have been uploaded): "lu_refactor_wide_kernel", "lu_refactor_rowlane_kernel",
  * "lu_refactor_panel_kernel", "lu_refactor_tmem_kernel" or "lu_refactor_kernel".  NULL on error. */

@@ -203,12 +203,14 @@ def test_dmma_dense_update_and_supernodes():
 @pytest.mark.parametrize("env", [{"CSP3_ROWLANE": "1", "CSP3_RL_W": "1"}, {"CSP3_ROWLANE": "1", "CSP3_RL_W": "2", "CSP3_RL_NQ": "1"},
                                  {"CSP3_ROWLANE": "1", "CSP3_RL_W": "2", "CSP3_RL_NQ": "2"}, {"CSP3_ROWLANE": "1", "CSP3_RL_W": "4", "CSP3_RL_NQ": "2"},
                                  {"CSP3_ROWLANE": "1", "CSP3_RL_W": "8"}, {"CSP3_ROWLANE": "1", "CSP3_RL_W": "4", "CSP3_RL_NQ": "2", "CSP3_RL_MARGIN": "-100000"},
-                                 {}])
+                                 {}, {"CSP3_ROWSWEEP": "1"}])
 def test_rowlane_refactor_geometries(env):
     """Row-lane refactor kernel (lu_rowlane.cu) with 1 / 2 / 4 / 8 warps per bundle, forced (CSP3_RL_W) and as the
     automatic choice for small batches: factors and solutions bit-identical to the oracle on the 118-bus, 2,000-bus and
     small irregular patterns, ragged batch sizes; a zero / non-finite pivot is reported with the oracle's code whichever
-    warp of the bundle eliminates that column.  The knobs are read once per process: child process."""
+    warp of the bundle eliminates that column.  CSP3_ROWSWEEP=1 additionally routes the triangular sweeps of these small
+    batches through the experimental row-oriented 8-warps-per-bundle kernel (lu_sweep_rows_kernel).  The knobs are read once
+    per process: child process."""
     code = (
         "import sys; sys.path.insert(0, %r); import numpy as np, torch, scipy.sparse as sp\n"
         "from csparse3_b200 import synth; from csparse3_b200.lu import LuSymbolic; from oracle import oracle as orc\n"
