@@ -46,6 +46,11 @@ def test_no_cpu_fallback_without_device():
     sym = LuSymbolic(n, Ap, Ai, Ax)
     with pytest.raises(_lib.Csp3Error, match="no CPU fallback"):
         sym.refactor_solve_host(Ax[None, :].copy(), np.ones((1, n)))
+    # the kernel-selection introspection needs an uploaded schedule: a NULL name and an error code, no crash
+    L = _lib.lib()
+    assert L.csp3_lu_refactor_kernel_name(sym._h, 8) is None
+    assert L.csp3_lu_prepare(sym._h, 8) != 0
+    assert b"not uploaded" in L.csp3_last_error_string()
 
 
 def test_dtype_strictness_like_reference():
