@@ -106,3 +106,41 @@ def test_rowlane_program_laplacians_many_warps():
     for env in ({"CSP3_RL_W": "8", "CSP3_RL_NQ": "1"}, {"CSP3_RL_W": "4", "CSP3_RL_NQ": "2"}):
         out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True)
         assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def _structured_cases():
+    rng = np.random.default_rng(7)
+    cases = []
+    n = 60; cases.append(sp.csc_matrix(rng.uniform(-1, 1, (n, n)) + np.eye(n) * n))                      # dense: overflow quads
+    n = 100; A = sp.lil_matrix((n, n)); A.setdiag(4.0); A[0, :] = 1.0; A[:, 0] = 1.0; A[n - 1, :] = 0.5; A[:, n - 1] = 0.5
+    A[n - 1, n - 1] = 9.0; cases.append(sp.csc_matrix(A))                                                 # arrow: fills in completely with order 0
+    n = 120; cases.append(sp.csc_matrix(sp.diags([rng.uniform(0.1, 1, n - abs(k)) for k in range(-9, 10)], list(range(-9, 10))) + sp.eye(n) * 30))
+    out = []
+    for A in cases:
+        A.sort_indices()
+        out.append((A.shape[0], A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()))
+    return out
+
+
+def test_rowlane_and_rowsweep_structured_patterns():
+    """Dense, arrow and banded matrices (columns with more than 8 entries of every role: STOREL4 / STOREU4 / LOAD4 quads)
+    through the row-lane refactor program (one warp per bundle here; 8 warps in the child process below) and the
+    row-sweep programs: bit-identical to the oracle."""
+    import rowsweep_interp as rs
+    rng = np.random.default_rng(1)
+    for n, Ap, Ai, Ax in _structured_cases():
+        for order in (0, 1):
+            Axb = Ax[None, :] * rng.uniform(0.95, 1.05, (2, len(Ax)))
+            sym, stats = _check(n, Ap, Ai, Axb, order=order)
+            Lx, Ux, _, _ = ri.run_refactor(sym, Axb)
+            b = rng.standard_normal((2, n))
+            x = rs.solve(sym, Lx, Ux, b)
+            for k in range(2):
+                assert np.array_equal(x[k], orc.csc_lu_solve(n, sym.Lp, sym.Li, Lx[k], sym.Up, sym.Ui, Ux[k], sym.pinv, sym.q, b[k]))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import numpy as np; import test_rowlane_program as t; "
+            "rng = np.random.default_rng(2)\n"
+            "for n, Ap, Ai, Ax in t._structured_cases():\n"
+            "    for order in (0, 1): t._check(n, Ap, Ai, Ax[None, :] * rng.uniform(0.95, 1.05, (2, len(Ax))), order=order)\n"
+            "print('ok')") % (ROOT, os.path.join(ROOT, "tests"))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CSP3_RL_W="8", CSP3_RL_NQ="1"), capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
